@@ -1,0 +1,5 @@
+"""B200-native batched contact-implicit interior-point path (drop-in for the MPC inner loop of
+dojo-sim/ContactImplicitMPC.jl).  The directory name carries a dot, so import it through the
+repo-root shim:  `import cimpc_b200`."""
+from .capi import LIB_PATH, SYMBOLS, CimpcError, load_library  # noqa: F401
+from .solver import ImplicitTrajectory, InteriorPointOptions, implicit_dynamics  # noqa: F401

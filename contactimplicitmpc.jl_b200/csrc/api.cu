@@ -1,0 +1,380 @@
+// C ABI (include/cimpc_b200.h): context, linearization upload + set-up kernel, batched solves.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "registry.cuh"
+
+using namespace cimpc;
+
+// ------------------------------------------------------------------------------------------
+// Set-up kernel: one CTA per reference knot.  Slices r0 / rz0 / rθ0 into the RLin / RZLin / RθLin
+// blocks (src/controller/linearized_solver.jl:92-120, 245-251, 346-348) and forms the constant
+// products of the Schur constructor (src/solver/schur.jl:33-49): Ai = Dx⁻¹ (Gauss-Jordan with
+// partial pivoting), CAi = Rx Ai, AiB = Ai Dy1, S0 = Ry1 − CAi Dy1, plus the θ-offset vectors and the
+// sensitivity right-hand sides W = CAi Rθdyn − Rθrst, AR = Ai Rθdyn used by ip_solve_kernel.
+// ------------------------------------------------------------------------------------------
+struct PrepParams {
+  LinLayout lay;
+  const double* z0;    // nz × H
+  const double* th0;   // nθ × H
+  const double* r0;    // nz × H
+  const double* rz0;   // nz × nz × H
+  const double* rth0;  // nz × nθ × H
+  double* lin;         // H × stride
+};
+
+__global__ void __launch_bounds__(128) prep_kernel(const PrepParams p) {
+  const LinLayout& a = p.lay;
+  const int nx = a.nx, ny = a.ny, nz = a.nz, nth = a.nth, ncol = a.ncol;
+  const int t = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const double* z0 = p.z0 + (size_t)t * nz;
+  const double* th0 = p.th0 + (size_t)t * nth;
+  const double* r0 = p.r0 + (size_t)t * nz;
+  const double* rz = p.rz0 + (size_t)t * nz * nz;
+  const double* rth = p.rth0 + (size_t)t * nz * nth;
+  double* L = p.lin + (size_t)t * a.stride;
+  // z = [x(nx); y1(ny); y2(ny)],  r = [dyn(nx); rst(ny); bil(ny)]   (index.jl:289-327)
+  const int ox = 0, oy1 = nx, oy2 = nx + ny, odyn = 0, orst = nx;
+
+  for (int e = tid; e < a.stride; e += nt) L[e] = 0.0;
+  __syncthreads();
+  for (int e = tid; e < nx * nx; e += nt) L[a.o_dx + e] = rz[(odyn + e % nx) + (size_t)(ox + e / nx) * nz];
+  for (int e = tid; e < nx * ny; e += nt) L[a.o_dy1 + e] = rz[(odyn + e % nx) + (size_t)(oy1 + e / nx) * nz];
+  for (int e = tid; e < ny * nx; e += nt) L[a.o_rx + e] = rz[(orst + e % ny) + (size_t)(ox + e / ny) * nz];
+  for (int e = tid; e < ny * ny; e += nt) L[a.o_ry1 + e] = rz[(orst + e % ny) + (size_t)(oy1 + e / ny) * nz];
+  for (int e = tid; e < ny; e += nt) L[a.o_ry2 + e] = rz[(orst + e) + (size_t)(oy2 + e) * nz];
+  for (int e = tid; e < nx * nth; e += nt) L[a.o_rtd + e] = rth[(odyn + e % nx) + (size_t)(e / nx) * nz];
+  for (int e = tid; e < ny * nth; e += nt) L[a.o_rtr + e] = rth[(orst + e % ny) + (size_t)(e / ny) * nz];
+  __syncthreads();
+
+  // ---- Ai = Dx⁻¹ by Gauss-Jordan on [Dx | I] in shared memory ----
+  extern __shared__ double sm[];
+  double* M = sm;  // nx × 2nx, row-major
+  __shared__ int s_piv;
+  const int w2 = 2 * nx;
+  for (int e = tid; e < nx * w2; e += nt) {
+    const int i = e / w2, j = e % w2;
+    M[e] = (j < nx) ? L[a.o_dx + i + j * nx] : ((j - nx == i) ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  for (int k = 0; k < nx; ++k) {
+    if (tid == 0) {
+      int best = k;
+      double bv = fabs(M[k * w2 + k]);
+      for (int i = k + 1; i < nx; ++i) {
+        const double v = fabs(M[i * w2 + k]);
+        if (v > bv) { bv = v; best = i; }
+      }
+      s_piv = best;
+    }
+    __syncthreads();
+    const int pr = s_piv;
+    if (pr != k) {
+      for (int j = tid; j < w2; j += nt) {
+        const double tmp = M[k * w2 + j];
+        M[k * w2 + j] = M[pr * w2 + j];
+        M[pr * w2 + j] = tmp;
+      }
+    }
+    __syncthreads();
+    const double pinv = 1.0 / M[k * w2 + k];
+    __syncthreads();
+    for (int j = tid; j < w2; j += nt) M[k * w2 + j] *= pinv;
+    __syncthreads();
+    for (int e = tid; e < nx * w2; e += nt) {
+      const int i = e / w2, j = e % w2;
+      if (i != k && j != k) M[e] = fma(-M[i * w2 + k], M[k * w2 + j], M[e]);
+    }
+    __syncthreads();
+    for (int i = tid; i < nx; i += nt)
+      if (i != k) M[i * w2 + k] = 0.0;
+    __syncthreads();
+  }
+  for (int e = tid; e < nx * nx; e += nt) L[a.o_ai + e] = M[(e % nx) * w2 + nx + e / nx];
+  __syncthreads();
+
+  // ---- constant products ----
+  for (int e = tid; e < ny * nx; e += nt) {  // CAi = Rx Ai
+    const int i = e % ny, j = e / ny;
+    double s = 0.0;
+    for (int k = 0; k < nx; ++k) s = fma(L[a.o_rx + i + k * ny], L[a.o_ai + k + j * nx], s);
+    L[a.o_cai + e] = s;
+  }
+  for (int e = tid; e < nx * ny; e += nt) {  // AiB = Ai Dy1
+    const int i = e % nx, j = e / nx;
+    double s = 0.0;
+    for (int k = 0; k < nx; ++k) s = fma(L[a.o_ai + i + k * nx], L[a.o_dy1 + k + j * nx], s);
+    L[a.o_aib + e] = s;
+  }
+  for (int e = tid; e < nx * ncol; e += nt) {  // AR = Ai Rθdyn[:, 1:ncol]
+    const int i = e % nx, j = e / nx;
+    double s = 0.0;
+    for (int k = 0; k < nx; ++k) s = fma(L[a.o_ai + i + k * nx], L[a.o_rtd + k + j * nx], s);
+    L[a.o_ar + e] = s;
+  }
+  for (int e = tid; e < nx; e += nt) {  // cdyn = rdyn0 − Dx x0 − Dy1 y10 − Rθdyn θ0
+    double s = r0[odyn + e];
+    for (int k = 0; k < nx; ++k) s = fma(-L[a.o_dx + e + k * nx], z0[ox + k], s);
+    for (int k = 0; k < ny; ++k) s = fma(-L[a.o_dy1 + e + k * nx], z0[oy1 + k], s);
+    for (int k = 0; k < nth; ++k) s = fma(-L[a.o_rtd + e + k * nx], th0[k], s);
+    L[a.o_cd + e] = s;
+  }
+  for (int e = tid; e < ny; e += nt) {  // crst = rrst0 − Rx x0 − Ry1 y10 − Ry2∘y20 − Rθrst θ0
+    double s = r0[orst + e];
+    for (int k = 0; k < nx; ++k) s = fma(-L[a.o_rx + e + k * ny], z0[ox + k], s);
+    for (int k = 0; k < ny; ++k) s = fma(-L[a.o_ry1 + e + k * ny], z0[oy1 + k], s);
+    s = fma(-L[a.o_ry2 + e], z0[oy2 + e], s);
+    for (int k = 0; k < nth; ++k) s = fma(-L[a.o_rtr + e + k * ny], th0[k], s);
+    L[a.o_cr + e] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < ny * ny; e += nt) {  // S0 = Ry1 − CAi Dy1
+    const int i = e % ny, j = e / ny;
+    double s = 0.0;
+    for (int k = 0; k < nx; ++k) s = fma(L[a.o_cai + i + k * ny], L[a.o_dy1 + k + j * nx], s);
+    L[a.o_s0 + e] = L[a.o_ry1 + e] - s;
+  }
+  for (int e = tid; e < ny * ncol; e += nt) {  // W = CAi Rθdyn − Rθrst  (first ncol columns)
+    const int i = e % ny, j = e / ny;
+    double s = 0.0;
+    for (int k = 0; k < nx; ++k) s = fma(L[a.o_cai + i + k * ny], L[a.o_rtd + k + j * nx], s);
+    L[a.o_w + e] = s - L[a.o_rtr + e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct cimpc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  const ModelEntry* entry = nullptr;
+  double* lin = nullptr;
+  int32_t h_ref = 0;
+  int64_t launches = 0;
+  std::string cuda_err;
+  // staging for the host entry point
+  void* pin = nullptr;   size_t pin_bytes = 0;
+  void* dev = nullptr;   size_t dev_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+};
+
+static int cuda_fail(cimpc_ctx* c, cudaError_t e, const char* where) {
+  if (c) c->cuda_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return CIMPC_ERR_CUDA;
+}
+#define CK(call)                                            \
+  do {                                                      \
+    cudaError_t e_ = (call);                                \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+  } while (0)
+
+static const ModelEntry* find_entry(const cimpc_model_desc& d) {
+#define CIMPC_SEARCH(name, nq, nu, nw, nc, nb)                                                   \
+  {                                                                                              \
+    int cnt = 0;                                                                                 \
+    const ModelEntry* e = entries_##name(&cnt);                                                  \
+    for (int i = 0; i < cnt; ++i)                                                                \
+      if (std::memcmp(&e[i].desc, &d, sizeof(cimpc_model_desc)) == 0) return &e[i];              \
+  }
+  CIMPC_FOR_EACH_MODEL(CIMPC_SEARCH)
+#undef CIMPC_SEARCH
+  return nullptr;
+}
+
+extern "C" {
+
+void cimpc_ip_opts_default(cimpc_ip_opts* o) {
+  if (!o) return;
+  o->r_tol = 1e-5; o->kappa_tol = 1e-5; o->eps_min = 0.05; o->kappa_reg = 1e-3; o->gamma_reg = 0.1;
+  o->undercut = 5.0; o->ls_scale = 0.5; o->max_iter = 100; o->max_ls = 3; o->diff_sol = 0; o->reserved = 0;
+}
+
+const char* cimpc_status_string(int s) {
+  switch (s) {
+    case CIMPC_OK: return "ok";
+    case CIMPC_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case CIMPC_ERR_UNSUPPORTED_MODEL: return "unsupported model dimensions (no compiled kernel instance)";
+    case CIMPC_ERR_NOT_INITIALIZED: return "linearization not uploaded";
+    case CIMPC_ERR_CUDA: return "CUDA error (see cimpc_last_cuda_error)";
+    case CIMPC_ERR_NO_DEVICE: return "no usable CUDA device";
+    default: return "unknown status";
+  }
+}
+
+const char* cimpc_last_cuda_error(const cimpc_ctx* ctx) { return ctx ? ctx->cuda_err.c_str() : ""; }
+int cimpc_version(void) { return CIMPC_B200_VERSION; }
+int64_t cimpc_launch_count(const cimpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cimpc_create(cimpc_ctx** out, int device, const cimpc_model_desc* desc) {
+  if (!out || !desc) return CIMPC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  const ModelEntry* e = find_entry(*desc);
+  if (!e) return CIMPC_ERR_UNSUPPORTED_MODEL;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return CIMPC_ERR_NO_DEVICE;
+  }
+  cimpc_ctx* ctx = new (std::nothrow) cimpc_ctx();
+  if (!ctx) return CIMPC_ERR_INVALID_ARGUMENT;
+  ctx->device = device;
+  ctx->entry = e;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return CIMPC_ERR_NO_DEVICE;
+  }
+  if (prop.major != 10) {  // sm_100a cubin only
+    delete ctx;
+    return CIMPC_ERR_NO_DEVICE;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return CIMPC_ERR_CUDA;
+  }
+  *out = ctx;
+  return CIMPC_OK;
+}
+
+int cimpc_destroy(cimpc_ctx* ctx) {
+  if (!ctx) return CIMPC_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->lin) cudaFree(ctx->lin);
+  if (ctx->dev) cudaFree(ctx->dev);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+  return CIMPC_OK;
+}
+
+int cimpc_get_dims(const cimpc_ctx* ctx, cimpc_dims* d) {
+  if (!ctx || !d) return CIMPC_ERR_INVALID_ARGUMENT;
+  const LinLayout& l = ctx->entry->lay;
+  d->nx = l.nx; d->ny = l.ny; d->nz = l.nz; d->ntheta = l.nth; d->nd = l.nd; d->ncol = l.ncol; d->group = l.group;
+  return CIMPC_OK;
+}
+
+int cimpc_upload_linearization(cimpc_ctx* ctx, int32_t H, const double* z0, const double* th0,
+                               const double* r0, const double* rz0, const double* rth0, void* stream) {
+  if (!ctx || H <= 0 || !z0 || !th0 || !r0 || !rz0 || !rth0) return CIMPC_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const LinLayout& l = ctx->entry->lay;
+  const size_t nz = l.nz, nth = l.nth;
+  const size_t n_z = nz * H, n_t = nth * H, n_rz = nz * nz * H, n_rt = nz * nth * H;
+  const size_t tot = 2 * n_z + n_t + n_rz + n_rt;
+  double* tmp = nullptr;
+  CK(cudaMalloc(&tmp, tot * sizeof(double)));
+  double* d_z0 = tmp; double* d_r0 = d_z0 + n_z; double* d_t0 = d_r0 + n_z; double* d_rz = d_t0 + n_t;
+  double* d_rt = d_rz + n_rz;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_z0, z0, n_z * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_r0, r0, n_z * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t0, th0, n_t * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rz, rz0, n_rz * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rt, rth0, n_rt * 8, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess && (ctx->h_ref != H || !ctx->lin)) {
+    if (ctx->lin) cudaFree(ctx->lin);
+    ctx->lin = nullptr;
+    ctx->h_ref = 0;
+    e = cudaMalloc(&ctx->lin, (size_t)H * l.stride * sizeof(double));
+  }
+  if (e == cudaSuccess) {
+    PrepParams pp{l, d_z0, d_t0, d_r0, d_rz, d_rt, ctx->lin};
+    const size_t smem = (size_t)l.nx * 2 * l.nx * sizeof(double);
+    prep_kernel<<<H, 128, smem, s>>>(pp);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cimpc_upload_linearization");
+  ctx->h_ref = H;
+  return CIMPC_OK;
+}
+
+static int check_solve_args(cimpc_ctx* ctx, int64_t n, const void* knot, const void* theta, const void* q2,
+                            const cimpc_ip_opts* o, const void* z, const void* dz, const void* st,
+                            const void* it) {
+  if (!ctx || n < 0 || !o) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (!ctx->lin || ctx->h_ref <= 0) return CIMPC_ERR_NOT_INITIALIZED;
+  if (n > 0 && (!knot || !theta || !q2 || !z || !st || !it)) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (n > 0 && o->diff_sol && !dz) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (o->max_iter < 0 || o->max_ls < 0) return CIMPC_ERR_INVALID_ARGUMENT;
+  return CIMPC_OK;
+}
+
+int cimpc_ip_solve_batch(cimpc_ctx* ctx, int64_t n, const int32_t* knot, const double* theta,
+                         const double* q2_init, const double* alt, const cimpc_ip_opts* opts,
+                         double* z_out, double* dz_out, uint8_t* status, int32_t* iters, void* stream) {
+  int rc = check_solve_args(ctx, n, knot, theta, q2_init, opts, z_out, dz_out, status, iters);
+  if (rc != CIMPC_OK) return rc;
+  if (n == 0) return CIMPC_OK;
+  CK(cudaSetDevice(ctx->device));
+  IpParams p;
+  p.n = n; p.knot = knot; p.theta = theta; p.q2_init = q2_init; p.alt = alt; p.lin = ctx->lin;
+  p.h_ref = ctx->h_ref; p.z_out = z_out; p.dz_out = dz_out; p.status = status; p.iters = iters; p.o = *opts;
+  cudaError_t e = ctx->entry->launch(p, ctx->sm_count, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "ip_solve_kernel launch");
+  ctx->launches++;
+  return CIMPC_OK;
+}
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, const double* theta,
+                              const double* q2_init, const double* alt, const cimpc_ip_opts* opts,
+                              double* z_out, double* dz_out, uint8_t* status, int32_t* iters) {
+  int rc = check_solve_args(ctx, n, knot, theta, q2_init, opts, z_out, dz_out, status, iters);
+  if (rc != CIMPC_OK) return rc;
+  if (n == 0) return CIMPC_OK;
+  for (int64_t i = 0; i < n; ++i)
+    if (knot[i] < 0 || knot[i] >= ctx->h_ref) return CIMPC_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  const LinLayout& l = ctx->entry->lay;
+  const int nc = ctx->entry->desc.nc;
+  const size_t b_knot = align256(n * 4), b_th = align256(n * l.nth * 8), b_q2 = align256(n * l.nx * 8);
+  const size_t b_alt = alt ? align256(n * nc * 8) : 0;
+  const size_t b_z = align256(n * l.nz * 8), b_dz = opts->diff_sol ? align256(n * (size_t)l.nd * l.ncol * 8) : 0;
+  const size_t b_st = align256(n), b_it = align256(n * 4);
+  const size_t in_bytes = b_knot + b_th + b_q2 + b_alt, out_bytes = b_z + b_dz + b_st + b_it;
+  const size_t tot = in_bytes + out_bytes;
+  if (ctx->pin_bytes < tot) {
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr; ctx->pin_bytes = 0;
+    CK(cudaMallocHost(&ctx->pin, tot));
+    ctx->pin_bytes = tot;
+  }
+  if (ctx->dev_bytes < tot) {
+    if (ctx->dev) cudaFree(ctx->dev);
+    ctx->dev = nullptr; ctx->dev_bytes = 0;
+    CK(cudaMalloc(&ctx->dev, tot));
+    ctx->dev_bytes = tot;
+  }
+  char* hp = (char*)ctx->pin;
+  char* dp = (char*)ctx->dev;
+  size_t o_knot = 0, o_th = o_knot + b_knot, o_q2 = o_th + b_th, o_alt = o_q2 + b_q2;
+  size_t o_z = in_bytes, o_dz = o_z + b_z, o_st = o_dz + b_dz, o_it = o_st + b_st;
+  std::memcpy(hp + o_knot, knot, n * 4);
+  std::memcpy(hp + o_th, theta, n * l.nth * 8);
+  std::memcpy(hp + o_q2, q2_init, n * l.nx * 8);
+  if (alt) std::memcpy(hp + o_alt, alt, n * nc * 8);
+  cudaStream_t s = ctx->own_stream;
+  CK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, s));
+  rc = cimpc_ip_solve_batch(ctx, n, (const int32_t*)(dp + o_knot), (const double*)(dp + o_th),
+                            (const double*)(dp + o_q2), alt ? (const double*)(dp + o_alt) : nullptr, opts,
+                            (double*)(dp + o_z), opts->diff_sol ? (double*)(dp + o_dz) : nullptr,
+                            (uint8_t*)(dp + o_st), (int32_t*)(dp + o_it), s);
+  if (rc != CIMPC_OK) return rc;
+  CK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, out_bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  std::memcpy(z_out, hp + o_z, n * l.nz * 8);
+  if (opts->diff_sol) std::memcpy(dz_out, hp + o_dz, n * (size_t)l.nd * l.ncol * 8);
+  std::memcpy(status, hp + o_st, n);
+  std::memcpy(iters, hp + o_it, n * 4);
+  return CIMPC_OK;
+}
+
+}  // extern "C"

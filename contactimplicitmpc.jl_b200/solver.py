@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's interface for the MPC inner loop.
+
+Names follow the reference (dojo-sim/ContactImplicitMPC.jl @ 989c8e6):
+  * `InteriorPointOptions`  — RoboDojo's options struct as used at `src/controller/policy.jl:54-61`
+  * `ImplicitTrajectory`    — `src/controller/implicit_dynamics.jl:6-90`: owns the per-knot linearized
+                              problems (here: one device-resident block store instead of H_ref Julia objects)
+  * `implicit_dynamics!`    — `src/controller/implicit_dynamics.jl:156-192`: here batched over
+                              (rollout × stage) subproblems in ONE kernel launch.
+All numerical work happens in the CUDA library behind the C ABI (`capi.py`); this file only
+marshals arrays.  numpy arrays go through the HOST entry point, torch CUDA tensors through the
+DEVICE entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class InteriorPointOptions:
+    r_tol: float = 1.0e-5
+    kappa_tol: float = 1.0e-5
+    max_iter: int = 100
+    max_ls: int = 3
+    ls_scale: float = 0.5
+    diff_sol: bool = False
+    eps_min: float = 0.05
+    kappa_reg: float = 1.0e-3
+    gamma_reg: float = 1.0e-1
+    undercut: float = 5.0
+
+    def to_c(self) -> capi.IPOpts:
+        return capi.IPOpts(self.r_tol, self.kappa_tol, self.eps_min, self.kappa_reg, self.gamma_reg,
+                           self.undercut, self.ls_scale, self.max_iter, self.max_ls, int(self.diff_sol), 0)
+
+
+MODES = {"configuration": 0, "configurationforce": 1}
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError(f"expected shape {tuple(shape)}, got {a.shape}")
+    return a
+
+
+class ImplicitTrajectory:
+    """Device-resident linearized contact problems of one robot (all H_ref reference knots).
+
+    Parameters mirror `ImplicitTrajectory(ref_traj, s; κ, opts, mode)`:
+      nq, nu, nw, nc, nb : model sizes (`s.model`, `friction_dim(env)`)
+      z0, th0, r0, rz0, rth0 : the `LinearizedStep` data of every knot, arrays with the knot
+          index FIRST (H, nz), (H, nθ), (H, nz), (H, nz, nz), (H, nz, nθ) in the usual numpy
+          row-major [i, j] meaning (they are transposed to Julia layout internally).
+    """
+
+    def __init__(self, nq, nu, nw, nc, nb, z0, th0, r0, rz0, rth0, *, mode="configuration",
+                 opts: InteriorPointOptions | None = None, device: int = 0):
+        self.lib = capi.load_library()
+        self.mode = mode
+        self.opts = opts or InteriorPointOptions(diff_sol=True)
+        self._ctx = C.c_void_p()
+        desc = capi.ModelDesc(nq, nu, nw, nc, nb, MODES[mode])
+        capi.check(None, self.lib.cimpc_create(C.byref(self._ctx), device, C.byref(desc)))
+        d = capi.Dims()
+        capi.check(self._ctx, self.lib.cimpc_get_dims(self._ctx, C.byref(d)))
+        self.nq, self.nu, self.nw, self.nc, self.nb = nq, nu, nw, nc, nb
+        self.nx, self.ny, self.nz, self.ntheta, self.nd, self.ncol = d.nx, d.ny, d.nz, d.ntheta, d.nd, d.ncol
+        self.group = d.group
+        self.device = device
+        self.H = 0
+        self.update(z0, th0, r0, rz0, rth0)
+
+    # -- set-up / re-linearization (`update!`, linearized_solver.jl:497-565) --
+    def update(self, z0, th0, r0, rz0, rth0):
+        H = np.asarray(z0).shape[0]
+        z0 = _f64(z0, (H, self.nz))
+        th0 = _f64(th0, (H, self.ntheta))
+        r0 = _f64(r0, (H, self.nz))
+        # numpy [t, i, j] row-major → Julia column-major nz×nz×H means [t][j][i] contiguous in i
+        rz0 = np.ascontiguousarray(np.transpose(_f64(rz0, (H, self.nz, self.nz)), (0, 2, 1)))
+        rth0 = np.ascontiguousarray(np.transpose(_f64(rth0, (H, self.nz, self.ntheta)), (0, 2, 1)))
+        capi.check(self._ctx, self.lib.cimpc_upload_linearization(
+            self._ctx, H, z0.ctypes.data, th0.ctypes.data, r0.ctypes.data, rz0.ctypes.data,
+            rth0.ctypes.data, None))
+        self.H = H
+
+    def close(self):
+        if self._ctx:
+            self.lib.cimpc_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.cimpc_launch_count(self._ctx))
+
+    # -- batched solve, HOST buffers --
+    def solve_host(self, knot, theta, q2_init, alt=None, opts: InteriorPointOptions | None = None):
+        """numpy in / numpy out through `cimpc_ip_solve_batch_host`.
+        Returns z (n, nz), dz (n, nd, ncol) or None, status (n,) bool, iters (n,) int32."""
+        o = (opts or self.opts)
+        knot = np.ascontiguousarray(knot, dtype=np.int32)
+        n = knot.shape[0]
+        theta = _f64(theta, (n, self.ntheta))
+        q2_init = _f64(q2_init, (n, self.nq))
+        alt_p = None
+        if alt is not None:
+            alt = _f64(alt, (n, self.nc))
+            alt_p = alt.ctypes.data
+        z = np.empty((n, self.nz))
+        dz = np.empty((n, self.ncol, self.nd)) if o.diff_sol else None
+        status = np.zeros(n, dtype=np.uint8)
+        iters = np.zeros(n, dtype=np.int32)
+        co = o.to_c()
+        capi.check(self._ctx, self.lib.cimpc_ip_solve_batch_host(
+            self._ctx, n, knot.ctypes.data, theta.ctypes.data, q2_init.ctypes.data, alt_p, C.byref(co),
+            z.ctypes.data, dz.ctypes.data if dz is not None else None, status.ctypes.data, iters.ctypes.data))
+        if dz is not None:
+            dz = np.transpose(dz, (0, 2, 1))  # column-major nd×ncol per problem → [n, row, col]
+        return z, dz, status.astype(bool), iters
+
+    # -- batched solve, DEVICE buffers (torch CUDA tensors; torch is plumbing only) --
+    def solve_device(self, knot, theta, q2_init, alt=None, out=None, opts: InteriorPointOptions | None = None,
+                     stream=None):
+        """torch CUDA tensors in / out through `cimpc_ip_solve_batch` (asynchronous on `stream`).
+        knot int32 (n,), theta (n, nθ), q2_init (n, nq), alt (n, nc) or None, all contiguous fp64.
+        `out` may hold preallocated (z, dz, status, iters).  dz is returned as (n, ncol, nd), i.e.
+        the per-problem column-major nd×ncol block of the C ABI."""
+        import torch
+        o = (opts or self.opts)
+        n = knot.shape[0]
+        assert knot.dtype == torch.int32 and knot.is_cuda and knot.is_contiguous()
+        for t_, w_ in ((theta, self.ntheta), (q2_init, self.nq)):
+            assert t_.dtype == torch.float64 and t_.is_cuda and t_.is_contiguous() and t_.shape == (n, w_)
+        if alt is not None:
+            assert alt.dtype == torch.float64 and alt.is_contiguous() and alt.shape == (n, self.nc)
+        dev = theta.device
+        if out is None:
+            z = torch.empty((n, self.nz), dtype=torch.float64, device=dev)
+            dz = torch.empty((n, self.ncol, self.nd), dtype=torch.float64, device=dev) if o.diff_sol else None
+            status = torch.empty(n, dtype=torch.uint8, device=dev)
+            iters = torch.empty(n, dtype=torch.int32, device=dev)
+        else:
+            z, dz, status, iters = out
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        co = o.to_c()
+        capi.check(self._ctx, self.lib.cimpc_ip_solve_batch(
+            self._ctx, n, knot.data_ptr(), theta.data_ptr(), q2_init.data_ptr(),
+            alt.data_ptr() if alt is not None else None, C.byref(co), z.data_ptr(),
+            dz.data_ptr() if dz is not None else None, status.data_ptr(), iters.data_ptr(),
+            C.c_void_p(stream)))
+        return z, dz, status, iters
+
+
+def implicit_dynamics(im_traj: ImplicitTrajectory, knot, theta, q2, gamma=None, b=None, alt=None,
+                      opts: InteriorPointOptions | None = None):
+    """`implicit_dynamics!(im_traj, traj; window)` for a flat batch of (rollout × stage) problems.
+
+    knot[i] = `window[i]` (0-based), theta[i] = `traj.θ[i]`, q2[i] = `traj.q[i+2]` (cold start and the
+    point the dynamics violation is measured against), gamma/b = `traj.γ[i]`, `traj.b[i]`
+    (:configurationforce only).  Returns d (n, nd), δq0 (n, nd, nq), δq1 (n, nd, nq), δu1 (n, nd, nu),
+    status, iters, z  — the `d`, `δq0`, `δq1`, `δu1` views of implicit_dynamics.jl:71-86.
+    """
+    z, dz, status, iters = im_traj.solve_host(knot, theta, q2, alt=alt, opts=opts)
+    nq, nc, nb, nu = im_traj.nq, im_traj.nc, im_traj.nb, im_traj.nu
+    d = z[:, :im_traj.nd].copy()
+    d[:, :nq] -= np.asarray(q2)
+    if im_traj.mode == "configurationforce":
+        d[:, nq:nq + nc] -= np.asarray(gamma)
+        d[:, nq + nc:nq + nc + nb] -= np.asarray(b)
+    if dz is None:
+        return d, None, None, None, status, iters, z
+    return d, dz[:, :, :nq], dz[:, :, nq:2 * nq], dz[:, :, 2 * nq:2 * nq + nu], status, iters, z
