@@ -79,27 +79,26 @@ def interior_point_solve(p: LinProblem, z: np.ndarray, th: np.ndarray, opts: IPO
         a_aff = step_length(y1, y2, d_aff[i.y1], d_aff[i.y2], 1.0)
         mu = float(np.dot(y1, y2)) / ny
         mu_aff = float(np.dot(y1 - a_aff * d_aff[i.y1], y2 - a_aff * d_aff[i.y2])) / ny
-        sigma = min(max(mu_aff / mu, 0.0), 1.0) ** 3
+        sigma = min(max(mu_aff / mu, 0.0), 1.0)
+        sigma = sigma * sigma * sigma  # Julia `^3` lowers to x*x*x (Base.literal_pow)
         # corrector residual: κ = max(σμ, κ_tol/undercut), plus Δaff_y1 ∘ Δaff_y2
         p.r(z, th, max(sigma * mu, opts.kappa_tol / opts.undercut))
         p.correction(d_aff)
         d = p.solve(reg=reg)
-        tau = max(1.0 - opts.eps_min, 1.0 - max(r_vio, k_vio) ** 2)
+        vmax = max(r_vio, k_vio)
+        tau = max(1.0 - opts.eps_min, 1.0 - vmax * vmax)
         alpha = step_length(y1, y2, d[i.y1], d[i.y2], tau)
-        # candidate + back-tracking on the violation
-        z_cand = z - alpha * d
+        # candidate + back-tracking on the violations: trial ls = 0..max_ls at α·ls_scale^ls, the
+        # last one is accepted unconditionally (max_ls failed trials exhaust the line search)
+        z_cand = z
         r_cand = k_cand = 0.0
-        for _ls in range(opts.max_ls):
+        for ls in range(opts.max_ls + 1):
+            z_cand = z - alpha * d
             p.r(z_cand, th, 0.0)
             r_cand, k_cand = p.r_vio(), p.k_vio()
-            if r_cand <= r_vio or k_cand <= k_vio:
+            if r_cand <= r_vio or k_cand <= k_vio or ls == opts.max_ls:
                 break
             alpha *= opts.ls_scale
-            z_cand = z - alpha * d
-        else:
-            if opts.max_ls > 0:
-                p.r(z_cand, th, 0.0)
-                r_cand, k_cand = p.r_vio(), p.k_vio()
         z = z_cand
         r_vio, k_vio = r_cand, k_cand
     status = bool(r_vio < opts.r_tol and k_vio < opts.kappa_tol)

@@ -63,16 +63,34 @@ class MGS:
         return x
 
 
+class DenseLU:
+    """NOT in the reference: LAPACK LU (partial pivoting) with the MGS interface.  Used by the tests as
+    the *accurate* variant of the oracle: the reference's MGS solve R⁻¹Qᵀb loses ≈ cond(S)²·eps, which on
+    ill-conditioned knots is far above fp64 round-off, so two faithful restatements of the reference
+    that differ only in summation order already disagree there (see tests/test_oracle.py)."""
+
+    def __init__(self, n: int):
+        self.n = n
+
+    def factorize(self, A: np.ndarray):
+        import scipy.linalg
+        self.lu = scipy.linalg.lu_factor(A)
+
+    def solve(self, b: np.ndarray) -> np.ndarray:
+        import scipy.linalg
+        return scipy.linalg.lu_solve(self.lu, b)
+
+
 # ------------------------------------------------------------------ Schur (schur.jl)
 class Schur:
     """[A B; C D] with constant A, B, C: caches A⁻¹, C A⁻¹, C A⁻¹ B (schur.jl:33-49)."""
 
-    def __init__(self, A, B, C, D):
+    def __init__(self, A, B, C, D, solver: str = "mgs"):
         self.A, self.B, self.C = A, B, C
         self.Ai = np.linalg.inv(A)           # schur.jl:39  `inv(A)`
         self.CAi = C @ self.Ai
         self.CAiB = C @ self.Ai @ B
-        self.gs = MGS(D.shape[0])
+        self.gs = MGS(D.shape[0]) if solver == "mgs" else DenseLU(D.shape[0])
         self.factorize(D)
 
     def factorize(self, D):  # schur_factorize!  schur.jl:80-88
@@ -141,14 +159,14 @@ class LinProblem:
     """One `InteriorPoint` object of `ImplicitTrajectory.ip[t]` with r = RLin, rz = RZLin, rθ = RθLin
     (implicit_dynamics.jl:58-68): the hooks the IP loop calls."""
 
-    def __init__(self, blk: LinBlocks, idx: Index):
+    def __init__(self, blk: LinBlocks, idx: Index, solver: str = "mgs"):
         self.b = blk
         self.idx = idx
         self.nz = idx.nz
         # RZLin ctor (linearized_solver.jl:253-258) builds the Schur object once; its initial
         # factorization (at the reference y1, y2) is always overwritten by rzlin! before any
         # solve, so the constant parts (A⁻¹, C A⁻¹, C A⁻¹ B) are all that matter here.
-        self.S = Schur(blk.Dx, blk.Dy1, blk.Rx, blk.Ry1 - np.eye(blk.ny))
+        self.S = Schur(blk.Dx, blk.Dy1, blk.Rx, blk.Ry1 - np.eye(blk.ny), solver=solver)
         self.y1 = blk.y10.copy()   # diag(rz0[bil, y2]) == y1 at z0  (:250)
         self.y2 = blk.y20.copy()   # diag(rz0[bil, y1]) == y2 at z0  (:251)
         self.rdyn = np.zeros(blk.nx)

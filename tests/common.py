@@ -58,15 +58,16 @@ class FixtureIndex:
         self.alt = self.imp
 
 
-def oracle_problems(robot: str, lin: dict):
-    """One oracle `LinProblem` per knot, built from the committed linearization fixture."""
+def oracle_problems(robot: str, lin: dict, solver: str = "mgs"):
+    """One oracle `LinProblem` per knot, built from the committed linearization fixture.
+    solver = "mgs" (the reference's QR) or "lu" (accurate variant, see oracle/linearized.py)."""
     from oracle.linearized import LinProblem, lin_blocks
     nq, nu, nw, nc, nb = SIZES[robot]
     idx = FixtureIndex(nq, nu, nw, nc, nb)
     probs = []
     for t in range(lin["z0"].shape[0]):
         blk = lin_blocks(idx, nc, lin["z0"][t], lin["th0"][t], lin["r0"][t], lin["rz0"][t], lin["rth0"][t])
-        probs.append(LinProblem(blk, idx))
+        probs.append(LinProblem(blk, idx, solver=solver))
     return idx, probs
 
 
@@ -86,11 +87,11 @@ def make_batch(robot: str, lin: dict, gait: dict, n: int, seed: int = 100, sigma
     return knot, theta, q2
 
 
-def oracle_solve_batch(robot, lin, knot, theta, q2, opts, alt=None, mode="configuration"):
+def oracle_solve_batch(robot, lin, knot, theta, q2, opts, alt=None, mode="configuration", solver="mgs"):
     """Run oracle/ip.py on every problem of the batch (slow: small n only)."""
     from oracle.ip import interior_point_solve
     nq, nu, nw, nc, nb = SIZES[robot]
-    idx, probs = oracle_problems(robot, lin)
+    idx, probs = oracle_problems(robot, lin, solver=solver)
     n = len(knot)
     nd = nq if mode == "configuration" else nq + nc + nb
     ncol = 2 * nq + nu
