@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py — contact-subproblems/s of the batched linearized interior-point sweep.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3              # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 2 ...    # the reference algorithm on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one `implicit_dynamics!` sweep (src/controller/implicit_dynamics.jl:156-192) over the
+whole Monte-Carlo batch: quadruped (`examples/quadruped/monte_carlo.jl:20-58`: gait2, H_mpc = 10,
+κ = 1e-4, IP r_tol = κ_tol = 1e-4, max_iter = 100, diff_sol), 65 536 rollouts × 10 stages = 655 360
+cold-started subproblems PER GPU, one kernel launch.  Weak scaling: every rank owns its own 64k
+rollouts (independent, no data-path collective); rank 0 only gathers iteration statistics.
+
+`value`   subproblems/s with inputs resident in HBM (device entry point of the C ABI).
+`e2e`     the same sweep through `cimpc_ip_solve_batch_host` with HOST (pinned) buffers: H2D of
+          (knot, θ, q2) and D2H of (z, δz, status, iters) inside the timed region.
+`roofline` HBM roofline of ip_solve_kernel from its algorithmic bytes (3 125 B per
+          quadruped subproblem) — structurally a few % because the path is fp64-issue bound; the
+          `fp64` object gives the companion fp64-FMA fraction.
+`cpu_baseline` the C restatement of the reference algorithm (oracle/c, MGS-QR, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ROBOT = "quadruped"
+MODE = "configuration"
+H_MPC = 10
+ROLLOUTS_PER_GPU = 65536
+IP_KW = dict(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, diff_sol=True)  # monte_carlo.jl:51-58
+METRIC = "contact_subproblems_per_sec"
+UNIT = "subproblems/s"
+
+
+def algorithmic_bytes(nq, nu, nw, nc, nb, mode):
+    """SURVEY.md §8d / BASELINE.md §3: read θ, q2 guess, alt; write d, δq0, δq1, δu1, status, iters."""
+    nth = 2 * nq + nu + nw + 2
+    nd = nq if mode == "configuration" else nq + nc + nb
+    return 8 * (nth + nq + nc) + 8 * (nd + nd * (2 * nq + nu)) + 5
+
+
+def algorithmic_flops(nq, nu, nc, nb, mean_iters):
+    """BASELINE.md §3 (reference algorithm's count: MGS 2ny³ per factorisation)."""
+    nx, ny = nq, 2 * nc + nb
+    f_it = 2 * ny ** 3 + ny ** 2 + 4 * (2 * nx * ny + 1.5 * ny ** 2 + nx ** 2) + 6 * (nx ** 2 + 2 * nx * ny + ny ** 2)
+    f_d = 2 * ny ** 3 + (2 * nq + nu) * 2 * (2 * nx * ny + 1.5 * ny ** 2 + nx ** 2)
+    return mean_iters * f_it + f_d
+
+
+def build_workload(rank: int, rollouts: int):
+    """Stage-major batch: subproblem (stage i, rollout r) uses knot i (all rollouts share the window,
+    policy.jl:100-107, 131) with rollout-specific perturbed θ and cold-start q2."""
+    from common import SIZES, load_gait, load_lin, make_batch
+    lin, gait = load_lin(ROBOT), load_gait(ROBOT)
+    n = rollouts * H_MPC
+    knot, theta, q2 = make_batch(ROBOT, lin, gait, n, seed=100 + rank)
+    # make_batch cycles knots 0..H_ref-1; restrict to the MPC window 0..H_MPC-1, stage-major
+    nq = SIZES[ROBOT][0]
+    stage = (np.arange(n) // rollouts).astype(np.int32)
+    theta = theta - lin["th0"][knot] + lin["th0"][stage]
+    q2 = q2 - lin["z0"][knot, :nq] + lin["z0"][stage, :nq]
+    return lin, stage, np.ascontiguousarray(theta), np.ascontiguousarray(q2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:  # region shorter than the sampling period: take the nearest sample
+            for ts, line in self.rows[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx = float(f[1])
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def fp64_peak():
+    """fp64 FMA peak measured by profiles/tools/fp64_peak.cu (committed summary), else nominal."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["dfma_tflops"]), "measured (profiles/fp64_peak.json)"
+    return 37.2, "nominal 148 SM x 64 DFMA/clk x 1.965 GHz"
+
+
+def cpu_baseline_run(lin, knot, theta, q2, sample: int, threads: int = 0):
+    from common import SIZES
+    from oracle.c_oracle import COracle
+    from oracle.ip import IPOptions
+    co = COracle(*SIZES[ROBOT], lin, mode=MODE, solver="mgs")
+    o = IPOptions(**IP_KW)
+    co.solve(knot[:2048], theta[:2048], q2[:2048], o, threads=threads)  # warm-up (page-in, thread pool)
+    t0 = time.perf_counter()
+    z, dz, st, it = co.solve(knot[:sample], theta[:sample], q2[:sample], o, threads=threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, co.max_threads if threads <= 0 else threads, dt, float(it.mean()), float(st.mean())
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's algorithm (C restatement: explicit Dx⁻¹, MGS-QR per
+    iteration, all nθ sensitivity columns) on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lin, knot, theta, q2 = build_workload(0, ROLLOUTS_PER_GPU // 8)
+    n = knot.shape[0]  # 81 920 subproblems per step (1/8 of the per-GPU batch)
+    from common import SIZES
+    from oracle.c_oracle import COracle
+    from oracle.ip import IPOptions
+    co = COracle(*SIZES[ROBOT], lin, mode=MODE, solver="mgs")
+    o = IPOptions(**IP_KW)
+    for _ in range(max(args.warmup, 1)):
+        co.solve(knot, theta, q2, o)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        z, dz, st, it = co.solve(knot, theta, q2, o)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    cores = co.max_threads
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"quadruped flat gait2 H_mpc=10 linearized IP sweep, bounded sample of "
+                               f"{n} subproblems/step of the 655360-subproblem batch", "mode": MODE, **IP_KW},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} subproblems x {args.steps} steps; C restatement of the Julia CPU path "
+                                   f"(oracle/c/ip_oracle.c, OpenMP over problems)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mean_ip_iterations": float(it.mean()), "converged_frac": float(st.mean()),
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rollouts", type=int, default=ROLLOUTS_PER_GPU, help="rollouts per GPU (default 65536)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import cimpc_b200 as cb
+    from common import SIZES
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    nq, nu, nw, nc, nb = SIZES[ROBOT]
+    lin, knot, theta, q2 = build_workload(rank, args.rollouts)
+    n = knot.shape[0]
+    opts = cb.InteriorPointOptions(**IP_KW)
+    im = cb.ImplicitTrajectory(nq, nu, nw, nc, nb, lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
+                               mode=MODE, opts=opts, device=local)
+
+    # ---- device-resident leg -------------------------------------------------------------
+    kd = torch.from_numpy(knot).to(dev)
+    td = torch.from_numpy(theta).to(dev)
+    qd = torch.from_numpy(q2).to(dev)
+    outb = im.solve_device(kd, td, qd)
+    for _ in range(args.warmup):
+        im.solve_device(kd, td, qd, out=outb)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = im.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    ev[0].record()
+    for s in range(args.steps):
+        im.solve_device(kd, td, qd, out=outb)
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if dist:
+        dist.barrier()
+    launches = im.launch_count - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    st = outb[2]
+    it = outb[3]
+    stats = torch.stack([st.double().mean(), it.double().mean(), it.double().max()])
+    if dist:
+        gathered = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(gathered, stats)
+        stats = torch.stack(gathered).mean(0)
+    conv_frac, mean_it, max_it = [float(x) for x in stats.cpu()]
+
+    # ---- end-to-end leg: host (pinned) buffers through cimpc_ip_solve_batch_host ---------------
+    e2e_steps = max(2, min(args.steps, 3))
+    knot_h = torch.from_numpy(knot).pin_memory()
+    theta_h = torch.from_numpy(theta).pin_memory()
+    q2_h = torch.from_numpy(q2).pin_memory()
+    z_h = torch.empty((n, im.nz), dtype=torch.float64).pin_memory()
+    dz_h = torch.empty((n, im.ncol, im.nd), dtype=torch.float64).pin_memory()
+    st_h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    it_h = torch.empty(n, dtype=torch.int32).pin_memory()
+    h2d = knot_h.numel() * 4 + theta_h.numel() * 8 + q2_h.numel() * 8
+    d2h = z_h.numel() * 8 + dz_h.numel() * 8 + st_h.numel() + it_h.numel() * 4
+
+    def e2e_once():
+        im.solve_host_into(knot_h.numpy(), theta_h.numpy(), q2_h.numpy(), None, z_h.numpy(), dz_h.numpy(),
+                           st_h.numpy(), it_h.numpy())
+
+    e2e_once()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_once()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_ok = bool(np.array_equal(z_h.numpy(), outb[0].cpu().numpy()))
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    value = n * world * args.steps / (total_ms_max * 1e-3)
+    kernel_ms = float(np.mean(per_launch_ms))
+    peaks, peak_kind = measured_peaks()
+    B = algorithmic_bytes(nq, nu, nw, nc, nb, MODE)
+    achieved = n * B / (kernel_ms * 1e-3) / 1e9
+    fl = algorithmic_flops(nq, nu, nc, nb, mean_it)
+    f_peak, f_kind = fp64_peak()
+    f_ach = n * fl / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ip_kernel_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"quadruped flat gait2, H_mpc={H_MPC}, {args.rollouts} Monte-Carlo rollouts per GPU = "
+                               f"{n} cold-started linearized IP subproblems per step per GPU (one implicit_dynamics! sweep)",
+                   "mode": MODE, **IP_KW, "l2": "inputs+outputs per step (2.2 GB) exceed the 126 MB L2",
+                   "parallelism": f"rollout-sharded x{world}, no data-path collective"},
+        "mean_ip_iterations": mean_it, "max_ip_iterations": max_it, "converged_frac": conv_frac,
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+        "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_device_leg": e2e_ok,
+                "api": "cimpc_ip_solve_batch_host (pinned host buffers, chunk-pipelined H2D / kernel / D2H)"},
+        "roofline": {"bound": "hbm", "kernel": "ip_solve_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                     "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "algorithmic_bytes_per_subproblem": B,
+                     "kernel_ms": kernel_ms,
+                     "note": "fp64-issue bound path: HBM fraction is structurally small (SURVEY.md §8d); see fp64"},
+        "fp64": {"achieved": f_ach, "peak": f_peak, "unit": "TFLOP/s", "frac": f_ach / f_peak,
+                 "flops_per_subproblem": fl, "peak_source": f_kind,
+                 "note": "flops counted as the REFERENCE algorithm would spend them (BASELINE.md §3)"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        sample = min(n, 262144)
+        v, cores, dt, mit, conv = cpu_baseline_run(lin, knot, theta, q2, sample)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"first {sample} subproblems of the same batch, {dt:.1f} s wall; C restatement "
+                                         f"of the Julia CPU path (explicit Dx^-1, MGS-QR per iteration, all n_theta "
+                                         f"sensitivity columns), OpenMP over problems",
+                               "mean_ip_iterations": mit, "converged_frac": conv}
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

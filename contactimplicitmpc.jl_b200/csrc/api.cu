@@ -156,7 +156,9 @@ struct cimpc_ctx {
   // staging for the host entry point
   void* pin = nullptr;   size_t pin_bytes = 0;
   void* dev = nullptr;   size_t dev_bytes = 0;
-  cudaStream_t own_stream = nullptr;
+  static constexpr int NS = 3;            // pipeline depth of the host entry point
+  static constexpr int64_t CHUNK = 32768;  // subproblems per pipelined chunk
+  cudaStream_t streams[NS] = {nullptr, nullptr, nullptr};
 };
 
 static int cuda_fail(cimpc_ctx* c, cudaError_t e, const char* where) {
@@ -230,10 +232,11 @@ int cimpc_create(cimpc_ctx** out, int device, const cimpc_model_desc* desc) {
     return CIMPC_ERR_NO_DEVICE;
   }
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
-    delete ctx;
-    return CIMPC_ERR_CUDA;
-  }
+  for (int i = 0; i < cimpc_ctx::NS; ++i)
+    if (cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return CIMPC_ERR_CUDA;
+    }
   *out = ctx;
   return CIMPC_OK;
 }
@@ -244,7 +247,8 @@ int cimpc_destroy(cimpc_ctx* ctx) {
   if (ctx->lin) cudaFree(ctx->lin);
   if (ctx->dev) cudaFree(ctx->dev);
   if (ctx->pin) cudaFreeHost(ctx->pin);
-  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  for (int i = 0; i < cimpc_ctx::NS; ++i)
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
   delete ctx;
   return CIMPC_OK;
 }
@@ -324,6 +328,20 @@ int cimpc_ip_solve_batch(cimpc_ctx* ctx, int64_t n, const int32_t* knot, const d
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Host-buffer entry point: the batch is cut into chunks that flow through NS streams, so the H2D copy
+// of chunk c+1, the kernel of chunk c and the D2H copy of chunk c−1 overlap.  Buffers that are already
+// page-locked (cudaHostAlloc / cudaHostRegister / CUDA.jl `pin`) are DMA'd in place; pageable ones are
+// staged through the context's pinned slots.
 int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, const double* theta,
                               const double* q2_init, const double* alt, const cimpc_ip_opts* opts,
                               double* z_out, double* dz_out, uint8_t* status, int32_t* iters) {
@@ -335,45 +353,80 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
   CK(cudaSetDevice(ctx->device));
   const LinLayout& l = ctx->entry->lay;
   const int nc = ctx->entry->desc.nc;
-  const size_t b_knot = align256(n * 4), b_th = align256(n * l.nth * 8), b_q2 = align256(n * l.nx * 8);
-  const size_t b_alt = alt ? align256(n * nc * 8) : 0;
-  const size_t b_z = align256(n * l.nz * 8), b_dz = opts->diff_sol ? align256(n * (size_t)l.nd * l.ncol * 8) : 0;
-  const size_t b_st = align256(n), b_it = align256(n * 4);
-  const size_t in_bytes = b_knot + b_th + b_q2 + b_alt, out_bytes = b_z + b_dz + b_st + b_it;
-  const size_t tot = in_bytes + out_bytes;
-  if (ctx->pin_bytes < tot) {
-    if (ctx->pin) cudaFreeHost(ctx->pin);
-    ctx->pin = nullptr; ctx->pin_bytes = 0;
-    CK(cudaMallocHost(&ctx->pin, tot));
-    ctx->pin_bytes = tot;
-  }
-  if (ctx->dev_bytes < tot) {
+  const bool diff = opts->diff_sol != 0;
+  constexpr int NS = cimpc_ctx::NS;
+  const int64_t C = n < cimpc_ctx::CHUNK ? n : cimpc_ctx::CHUNK;  // subproblems per chunk
+  // per-slot layout (bytes)
+  const size_t b_knot = align256(C * 4), b_th = align256(C * l.nth * 8), b_q2 = align256(C * l.nx * 8);
+  const size_t b_alt = alt ? align256(C * nc * 8) : 0;
+  const size_t b_z = align256(C * l.nz * 8), b_dz = diff ? align256(C * (size_t)l.nd * l.ncol * 8) : 0;
+  const size_t b_st = align256(C), b_it = align256(C * 4);
+  const size_t o_knot = 0, o_th = o_knot + b_knot, o_q2 = o_th + b_th, o_alt = o_q2 + b_q2;
+  const size_t o_z = o_alt + b_alt, o_dz = o_z + b_z, o_st = o_dz + b_dz, o_it = o_st + b_st;
+  const size_t slot = o_it + b_it;
+  const bool pin_in = is_pinned(knot) && is_pinned(theta) && is_pinned(q2_init) && is_pinned(alt);
+  const bool pin_out = is_pinned(z_out) && (!diff || is_pinned(dz_out)) && is_pinned(status) && is_pinned(iters);
+  if (ctx->dev_bytes < slot * NS) {
     if (ctx->dev) cudaFree(ctx->dev);
     ctx->dev = nullptr; ctx->dev_bytes = 0;
-    CK(cudaMalloc(&ctx->dev, tot));
-    ctx->dev_bytes = tot;
+    CK(cudaMalloc(&ctx->dev, slot * NS));
+    ctx->dev_bytes = slot * NS;
   }
-  char* hp = (char*)ctx->pin;
-  char* dp = (char*)ctx->dev;
-  size_t o_knot = 0, o_th = o_knot + b_knot, o_q2 = o_th + b_th, o_alt = o_q2 + b_q2;
-  size_t o_z = in_bytes, o_dz = o_z + b_z, o_st = o_dz + b_dz, o_it = o_st + b_st;
-  std::memcpy(hp + o_knot, knot, n * 4);
-  std::memcpy(hp + o_th, theta, n * l.nth * 8);
-  std::memcpy(hp + o_q2, q2_init, n * l.nx * 8);
-  if (alt) std::memcpy(hp + o_alt, alt, n * nc * 8);
-  cudaStream_t s = ctx->own_stream;
-  CK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, s));
-  rc = cimpc_ip_solve_batch(ctx, n, (const int32_t*)(dp + o_knot), (const double*)(dp + o_th),
-                            (const double*)(dp + o_q2), alt ? (const double*)(dp + o_alt) : nullptr, opts,
-                            (double*)(dp + o_z), opts->diff_sol ? (double*)(dp + o_dz) : nullptr,
-                            (uint8_t*)(dp + o_st), (int32_t*)(dp + o_it), s);
-  if (rc != CIMPC_OK) return rc;
-  CK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, out_bytes, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  std::memcpy(z_out, hp + o_z, n * l.nz * 8);
-  if (opts->diff_sol) std::memcpy(dz_out, hp + o_dz, n * (size_t)l.nd * l.ncol * 8);
-  std::memcpy(status, hp + o_st, n);
-  std::memcpy(iters, hp + o_it, n * 4);
+  if ((!pin_in || !pin_out) && ctx->pin_bytes < slot * NS) {
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr; ctx->pin_bytes = 0;
+    CK(cudaMallocHost(&ctx->pin, slot * NS));
+    ctx->pin_bytes = slot * NS;
+  }
+  const int64_t nchunks = (n + C - 1) / C;
+  auto drain = [&](int64_t c) {  // copy staged outputs of chunk c to the caller (pageable outputs only)
+    const int64_t lo = c * C, m = (n - lo < C) ? (n - lo) : C;
+    const char* hp = (const char*)ctx->pin + (size_t)(c % NS) * slot;
+    std::memcpy(z_out + lo * l.nz, hp + o_z, m * l.nz * 8);
+    if (diff) std::memcpy(dz_out + lo * (size_t)l.nd * l.ncol, hp + o_dz, m * (size_t)l.nd * l.ncol * 8);
+    std::memcpy(status + lo, hp + o_st, m);
+    std::memcpy(iters + lo, hp + o_it, m * 4);
+  };
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int sl = (int)(c % NS);
+    cudaStream_t s = ctx->streams[sl];
+    if (c >= NS) {
+      CK(cudaStreamSynchronize(s));
+      if (!pin_out) drain(c - NS);
+    }
+    const int64_t lo = c * C, m = (n - lo < C) ? (n - lo) : C;
+    char* dp = (char*)ctx->dev + (size_t)sl * slot;
+    char* hp = ctx->pin ? (char*)ctx->pin + (size_t)sl * slot : nullptr;
+    const void *s_knot = knot + lo, *s_th = theta + lo * l.nth, *s_q2 = q2_init + lo * l.nx;
+    const void* s_alt = alt ? alt + lo * nc : nullptr;
+    if (!pin_in) {
+      std::memcpy(hp + o_knot, s_knot, m * 4); s_knot = hp + o_knot;
+      std::memcpy(hp + o_th, s_th, m * l.nth * 8); s_th = hp + o_th;
+      std::memcpy(hp + o_q2, s_q2, m * l.nx * 8); s_q2 = hp + o_q2;
+      if (alt) { std::memcpy(hp + o_alt, s_alt, m * nc * 8); s_alt = hp + o_alt; }
+    }
+    CK(cudaMemcpyAsync(dp + o_knot, s_knot, m * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dp + o_th, s_th, m * l.nth * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dp + o_q2, s_q2, m * l.nx * 8, cudaMemcpyHostToDevice, s));
+    if (alt) CK(cudaMemcpyAsync(dp + o_alt, s_alt, m * nc * 8, cudaMemcpyHostToDevice, s));
+    rc = cimpc_ip_solve_batch(ctx, m, (const int32_t*)(dp + o_knot), (const double*)(dp + o_th),
+                              (const double*)(dp + o_q2), alt ? (const double*)(dp + o_alt) : nullptr, opts,
+                              (double*)(dp + o_z), diff ? (double*)(dp + o_dz) : nullptr, (uint8_t*)(dp + o_st),
+                              (int32_t*)(dp + o_it), s);
+    if (rc != CIMPC_OK) return rc;
+    void* t_z = pin_out ? (void*)(z_out + lo * l.nz) : (void*)(hp + o_z);
+    void* t_dz = !diff ? nullptr : (pin_out ? (void*)(dz_out + lo * (size_t)l.nd * l.ncol) : (void*)(hp + o_dz));
+    void* t_st = pin_out ? (void*)(status + lo) : (void*)(hp + o_st);
+    void* t_it = pin_out ? (void*)(iters + lo) : (void*)(hp + o_it);
+    CK(cudaMemcpyAsync(t_z, dp + o_z, m * l.nz * 8, cudaMemcpyDeviceToHost, s));
+    if (diff) CK(cudaMemcpyAsync(t_dz, dp + o_dz, m * (size_t)l.nd * l.ncol * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(t_st, dp + o_st, m, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(t_it, dp + o_it, m * 4, cudaMemcpyDeviceToHost, s));
+  }
+  for (int64_t c = (nchunks > NS ? nchunks - NS : 0); c < nchunks; ++c) {
+    CK(cudaStreamSynchronize(ctx->streams[c % NS]));
+    if (!pin_out) drain(c);
+  }
   return CIMPC_OK;
 }
 

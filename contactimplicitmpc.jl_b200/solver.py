@@ -129,6 +129,24 @@ class ImplicitTrajectory:
             dz = np.transpose(dz, (0, 2, 1))  # column-major nd×ncol per problem → [n, row, col]
         return z, dz, status.astype(bool), iters
 
+    def solve_host_into(self, knot, theta, q2_init, alt, z, dz, status, iters,
+                        opts: InteriorPointOptions | None = None):
+        """Same call writing into caller-owned numpy arrays (e.g. views of pinned torch tensors):
+        z (n, nz), dz (n, ncol, nd) [the C ABI's per-problem column-major nd×ncol], status uint8, iters int32."""
+        o = (opts or self.opts)
+        n = knot.shape[0]
+        for a in (knot, theta, q2_init, z, status, iters):
+            assert a.flags["C_CONTIGUOUS"]
+        assert knot.dtype == np.int32 and status.dtype == np.uint8 and iters.dtype == np.int32
+        assert theta.shape == (n, self.ntheta) and q2_init.shape == (n, self.nq) and z.shape == (n, self.nz)
+        if o.diff_sol:
+            assert dz is not None and dz.shape == (n, self.ncol, self.nd) and dz.flags["C_CONTIGUOUS"]
+        co = o.to_c()
+        capi.check(self._ctx, self.lib.cimpc_ip_solve_batch_host(
+            self._ctx, n, knot.ctypes.data, theta.ctypes.data, q2_init.ctypes.data,
+            alt.ctypes.data if alt is not None else None, C.byref(co), z.ctypes.data,
+            dz.ctypes.data if (dz is not None and o.diff_sol) else None, status.ctypes.data, iters.ctypes.data))
+
     # -- batched solve, DEVICE buffers (torch CUDA tensors; torch is plumbing only) --
     def solve_device(self, knot, theta, q2_init, alt=None, out=None, opts: InteriorPointOptions | None = None,
                      stream=None):
