@@ -27,7 +27,7 @@ struct PrepParams {
 
 __global__ void __launch_bounds__(128) prep_kernel(const PrepParams p) {
   const LinLayout& a = p.lay;
-  const int nx = a.nx, ny = a.ny, nz = a.nz, nth = a.nth, ncol = a.ncol;
+  const int nx = a.nx, ny = a.ny, nz = a.nz, nth = a.nth, ncol = a.ncol, G = a.group;
   const int t = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const double* z0 = p.z0 + (size_t)t * nz;
   const double* th0 = p.th0 + (size_t)t * nth;
@@ -38,25 +38,37 @@ __global__ void __launch_bounds__(128) prep_kernel(const PrepParams p) {
   // z = [x(nx); y1(ny); y2(ny)],  r = [dyn(nx); rst(ny); bil(ny)]   (index.jl:289-327)
   const int ox = 0, oy1 = nx, oy2 = nx + ny, odyn = 0, orst = nx;
 
+  // dense column-major work copies in shared memory
+  extern __shared__ double sm[];
+  double* Dx = sm;                 // nx×nx
+  double* Dy1 = Dx + nx * nx;      // nx×ny
+  double* Rx = Dy1 + nx * ny;      // ny×nx
+  double* Ry1 = Rx + ny * nx;      // ny×ny
+  double* Ry2 = Ry1 + ny * ny;     // ny
+  double* Rtd = Ry2 + ny;          // nx×nth
+  double* Rtr = Rtd + nx * nth;    // ny×nth
+  double* Ai = Rtr + ny * nth;     // nx×nx
+  double* CAi = Ai + nx * nx;      // ny×nx
+  double* AiB = CAi + ny * nx;     // nx×ny
+  double* S0 = AiB + nx * ny;      // ny×ny
+  double* M = S0 + ny * ny;        // nx×2nx (Gauss-Jordan work, row-major)
+  __shared__ int s_piv;
+
   for (int e = tid; e < a.stride; e += nt) L[e] = 0.0;
-  __syncthreads();
-  for (int e = tid; e < nx * nx; e += nt) L[a.o_dx + e] = rz[(odyn + e % nx) + (size_t)(ox + e / nx) * nz];
-  for (int e = tid; e < nx * ny; e += nt) L[a.o_dy1 + e] = rz[(odyn + e % nx) + (size_t)(oy1 + e / nx) * nz];
-  for (int e = tid; e < ny * nx; e += nt) L[a.o_rx + e] = rz[(orst + e % ny) + (size_t)(ox + e / ny) * nz];
-  for (int e = tid; e < ny * ny; e += nt) L[a.o_ry1 + e] = rz[(orst + e % ny) + (size_t)(oy1 + e / ny) * nz];
-  for (int e = tid; e < ny; e += nt) L[a.o_ry2 + e] = rz[(orst + e) + (size_t)(oy2 + e) * nz];
-  for (int e = tid; e < nx * nth; e += nt) L[a.o_rtd + e] = rth[(odyn + e % nx) + (size_t)(e / nx) * nz];
-  for (int e = tid; e < ny * nth; e += nt) L[a.o_rtr + e] = rth[(orst + e % ny) + (size_t)(e / ny) * nz];
+  for (int e = tid; e < nx * nx; e += nt) Dx[e] = rz[(odyn + e % nx) + (size_t)(ox + e / nx) * nz];
+  for (int e = tid; e < nx * ny; e += nt) Dy1[e] = rz[(odyn + e % nx) + (size_t)(oy1 + e / nx) * nz];
+  for (int e = tid; e < ny * nx; e += nt) Rx[e] = rz[(orst + e % ny) + (size_t)(ox + e / ny) * nz];
+  for (int e = tid; e < ny * ny; e += nt) Ry1[e] = rz[(orst + e % ny) + (size_t)(oy1 + e / ny) * nz];
+  for (int e = tid; e < ny; e += nt) Ry2[e] = rz[(orst + e) + (size_t)(oy2 + e) * nz];
+  for (int e = tid; e < nx * nth; e += nt) Rtd[e] = rth[(odyn + e % nx) + (size_t)(e / nx) * nz];
+  for (int e = tid; e < ny * nth; e += nt) Rtr[e] = rth[(orst + e % ny) + (size_t)(e / ny) * nz];
   __syncthreads();
 
-  // ---- Ai = Dx⁻¹ by Gauss-Jordan on [Dx | I] in shared memory ----
-  extern __shared__ double sm[];
-  double* M = sm;  // nx × 2nx, row-major
-  __shared__ int s_piv;
+  // ---- Ai = Dx⁻¹ by Gauss-Jordan with partial pivoting on [Dx | I] ----
   const int w2 = 2 * nx;
   for (int e = tid; e < nx * w2; e += nt) {
     const int i = e / w2, j = e % w2;
-    M[e] = (j < nx) ? L[a.o_dx + i + j * nx] : ((j - nx == i) ? 1.0 : 0.0);
+    M[e] = (j < nx) ? Dx[i + j * nx] : ((j - nx == i) ? 1.0 : 0.0);
   }
   __syncthreads();
   for (int k = 0; k < nx; ++k) {
@@ -92,55 +104,93 @@ __global__ void __launch_bounds__(128) prep_kernel(const PrepParams p) {
       if (i != k) M[i * w2 + k] = 0.0;
     __syncthreads();
   }
-  for (int e = tid; e < nx * nx; e += nt) L[a.o_ai + e] = M[(e % nx) * w2 + nx + e / nx];
+  for (int e = tid; e < nx * nx; e += nt) Ai[e] = M[(e % nx) * w2 + nx + e / nx];
   __syncthreads();
 
-  // ---- constant products ----
+  // ---- constant products (schur.jl:39-41) ----
   for (int e = tid; e < ny * nx; e += nt) {  // CAi = Rx Ai
     const int i = e % ny, j = e / ny;
     double s = 0.0;
-    for (int k = 0; k < nx; ++k) s = fma(L[a.o_rx + i + k * ny], L[a.o_ai + k + j * nx], s);
-    L[a.o_cai + e] = s;
+    for (int k = 0; k < nx; ++k) s = fma(Rx[i + k * ny], Ai[k + j * nx], s);
+    CAi[e] = s;
   }
   for (int e = tid; e < nx * ny; e += nt) {  // AiB = Ai Dy1
     const int i = e % nx, j = e / nx;
     double s = 0.0;
-    for (int k = 0; k < nx; ++k) s = fma(L[a.o_ai + i + k * nx], L[a.o_dy1 + k + j * nx], s);
-    L[a.o_aib + e] = s;
-  }
-  for (int e = tid; e < nx * ncol; e += nt) {  // AR = Ai Rθdyn[:, 1:ncol]
-    const int i = e % nx, j = e / nx;
-    double s = 0.0;
-    for (int k = 0; k < nx; ++k) s = fma(L[a.o_ai + i + k * nx], L[a.o_rtd + k + j * nx], s);
-    L[a.o_ar + e] = s;
-  }
-  for (int e = tid; e < nx; e += nt) {  // cdyn = rdyn0 − Dx x0 − Dy1 y10 − Rθdyn θ0
-    double s = r0[odyn + e];
-    for (int k = 0; k < nx; ++k) s = fma(-L[a.o_dx + e + k * nx], z0[ox + k], s);
-    for (int k = 0; k < ny; ++k) s = fma(-L[a.o_dy1 + e + k * nx], z0[oy1 + k], s);
-    for (int k = 0; k < nth; ++k) s = fma(-L[a.o_rtd + e + k * nx], th0[k], s);
-    L[a.o_cd + e] = s;
-  }
-  for (int e = tid; e < ny; e += nt) {  // crst = rrst0 − Rx x0 − Ry1 y10 − Ry2∘y20 − Rθrst θ0
-    double s = r0[orst + e];
-    for (int k = 0; k < nx; ++k) s = fma(-L[a.o_rx + e + k * ny], z0[ox + k], s);
-    for (int k = 0; k < ny; ++k) s = fma(-L[a.o_ry1 + e + k * ny], z0[oy1 + k], s);
-    s = fma(-L[a.o_ry2 + e], z0[oy2 + e], s);
-    for (int k = 0; k < nth; ++k) s = fma(-L[a.o_rtr + e + k * ny], th0[k], s);
-    L[a.o_cr + e] = s;
+    for (int k = 0; k < nx; ++k) s = fma(Ai[i + k * nx], Dy1[k + j * nx], s);
+    AiB[e] = s;
   }
   __syncthreads();
   for (int e = tid; e < ny * ny; e += nt) {  // S0 = Ry1 − CAi Dy1
     const int i = e % ny, j = e / ny;
     double s = 0.0;
-    for (int k = 0; k < nx; ++k) s = fma(L[a.o_cai + i + k * ny], L[a.o_dy1 + k + j * nx], s);
-    L[a.o_s0 + e] = L[a.o_ry1 + e] - s;
+    for (int k = 0; k < nx; ++k) s = fma(CAi[i + k * ny], Dy1[k + j * nx], s);
+    S0[e] = Ry1[e] - s;
   }
-  for (int e = tid; e < ny * ncol; e += nt) {  // W = CAi Rθdyn − Rθrst  (first ncol columns)
+  __syncthreads();
+
+  // ---- packed, lane-major output layout (dims.cuh) ----
+  for (int e = tid; e < (nx + ny) * G; e += nt) {  // RES: {[Dx Dy1][l][j], [Rx Ry1][l][j]}
+    const int l = e % G, j = e / G;
+    double d = 0.0, r = 0.0;
+    if (j < nx) {
+      if (l < nx) d = Dx[l + j * nx];
+      if (l < ny) r = Rx[l + j * ny];
+    } else {
+      if (l < nx) d = Dy1[l + (j - nx) * nx];
+      if (l < ny) r = Ry1[l + (j - nx) * ny];
+    }
+    L[a.o_res + 2 * e] = d;
+    L[a.o_res + 2 * e + 1] = r;
+  }
+  for (int e = tid; e < nx * G; e += nt) {  // CA2: {CAi[l][j], Ai[l][j]}; AIBR: AiB[i][l]
+    const int l = e % G, j = e / G;
+    L[a.o_ca2 + 2 * e] = (l < ny) ? CAi[l + j * ny] : 0.0;
+    L[a.o_ca2 + 2 * e + 1] = (l < nx) ? Ai[l + j * nx] : 0.0;
+    L[a.o_aibr + e] = (l < ny) ? AiB[j + l * nx] : 0.0;
+  }
+  for (int e = tid; e < ny * G; e += nt) {  // AIBC: AiB[l][j]; S0, S0T
+    const int l = e % G, j = e / G;
+    L[a.o_aibc + e] = (l < nx) ? AiB[l + j * nx] : 0.0;
+    L[a.o_s0 + e] = (l < ny) ? S0[l + j * ny] : 0.0;
+    L[a.o_s0t + e] = (l < ny) ? S0[j + l * ny] : 0.0;
+  }
+  for (int e = tid; e < G; e += nt) L[a.o_ry2 + e] = (e < ny) ? Ry2[e] : 0.0;
+  for (int e = tid; e < ny * ncol; e += nt) {  // W = CAi Rθdyn − Rθrst  (first ncol columns), W[k][c] at c*ny + k
     const int i = e % ny, j = e / ny;
     double s = 0.0;
-    for (int k = 0; k < nx; ++k) s = fma(L[a.o_cai + i + k * ny], L[a.o_rtd + k + j * nx], s);
-    L[a.o_w + e] = s - L[a.o_rtr + e];
+    for (int k = 0; k < nx; ++k) s = fma(CAi[i + k * ny], Rtd[k + j * nx], s);
+    L[a.o_w + e] = s - Rtr[e];
+  }
+  for (int e = tid; e < ncol * G; e += nt) {  // AR = Ai Rθdyn[:, 1:ncol], AR[l][c] at c*G + l
+    const int l = e % G, j = e / G;
+    double s = 0.0;
+    if (l < nx)
+      for (int k = 0; k < nx; ++k) s = fma(Ai[l + k * nx], Rtd[k + j * nx], s);
+    L[a.o_ar + e] = s;
+  }
+  for (int e = tid; e < G; e += nt) {  // C0: {cdyn0, crst0}
+    double cd = 0.0, cr = 0.0;
+    if (e < nx) {  // cdyn = rdyn0 − Dx x0 − Dy1 y10 − Rθdyn θ0
+      cd = r0[odyn + e];
+      for (int k = 0; k < nx; ++k) cd = fma(-Dx[e + k * nx], z0[ox + k], cd);
+      for (int k = 0; k < ny; ++k) cd = fma(-Dy1[e + k * nx], z0[oy1 + k], cd);
+      for (int k = 0; k < nth; ++k) cd = fma(-Rtd[e + k * nx], th0[k], cd);
+    }
+    if (e < ny) {  // crst = rrst0 − Rx x0 − Ry1 y10 − Ry2∘y20 − Rθrst θ0
+      cr = r0[orst + e];
+      for (int k = 0; k < nx; ++k) cr = fma(-Rx[e + k * ny], z0[ox + k], cr);
+      for (int k = 0; k < ny; ++k) cr = fma(-Ry1[e + k * ny], z0[oy1 + k], cr);
+      cr = fma(-Ry2[e], z0[oy2 + e], cr);
+      for (int k = 0; k < nth; ++k) cr = fma(-Rtr[e + k * ny], th0[k], cr);
+    }
+    L[a.o_c0 + 2 * e] = cd;
+    L[a.o_c0 + 2 * e + 1] = cr;
+  }
+  for (int e = tid; e < nth * G; e += nt) {  // RTH: {Rθdyn[l][j], Rθrst[l][j]}
+    const int l = e % G, j = e / G;
+    L[a.o_rth + 2 * e] = (l < nx) ? Rtd[l + j * nx] : 0.0;
+    L[a.o_rth + 2 * e + 1] = (l < ny) ? Rtr[l + j * ny] : 0.0;
   }
 }
 
@@ -287,8 +337,11 @@ int cimpc_upload_linearization(cimpc_ctx* ctx, int32_t H, const double* z0, cons
   }
   if (e == cudaSuccess) {
     PrepParams pp{l, d_z0, d_t0, d_r0, d_rz, d_rt, ctx->lin};
-    const size_t smem = (size_t)l.nx * 2 * l.nx * sizeof(double);
-    prep_kernel<<<H, 128, smem, s>>>(pp);
+    const size_t smem = sizeof(double) * ((size_t)4 * l.nx * l.nx + 4 * l.nx * l.ny + 2 * l.ny * l.ny + l.ny +
+                                          (size_t)(l.nx + l.ny) * l.nth + 16);
+    if (e == cudaSuccess && smem > 48 * 1024)
+      e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) prep_kernel<<<H, 128, smem, s>>>(pp);
     ctx->launches++;
     e = cudaGetLastError();
   }

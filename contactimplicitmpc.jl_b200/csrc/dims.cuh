@@ -1,5 +1,5 @@
 // Compile-time sizes of one robot's linearized contact subproblem, and the layout of the
-// per-knot constant block ("LinStore") in HBM.
+// per-knot constant block ("LinStore") in HBM / shared memory.
 //
 // Sizes follow src/simulation/index.jl:371-390 (num_var, num_data) and
 // src/controller/linearized_solver.jl:78-80 (nx = nq, ny = 2nc + nb) of the reference.
@@ -29,25 +29,31 @@ struct Dims {
   // lanes cooperating on one subproblem: one lane per row of x / y1 / y2
   static constexpr int G = imax(4, pow2_ceil(imax(NX, NY)));
   static_assert(G <= 32, "subproblem rows must fit one warp");
+  static_assert(NX <= NY, "row padding below assumes nx <= ny");
+  static_assert(NY % 4 == 0, "Gauss-Jordan block size");
 
-  // ---- LinStore: per-knot constants, all column-major fp64, offsets in doubles ----
-  static constexpr int O_DX = 0;                        // Dx      NX×NX   rz0[dyn, x]
-  static constexpr int O_DY1 = O_DX + NX * NX;          // Dy1     NX×NY   rz0[dyn, y1]
-  static constexpr int O_RX = O_DY1 + NX * NY;          // Rx      NY×NX   rz0[rst, x]
-  static constexpr int O_RY1 = O_RX + NY * NX;          // Ry1     NY×NY   rz0[rst, y1]
-  static constexpr int O_RY2 = O_RY1 + NY * NY;         // Ry2     NY      diag rz0[rst, y2]
-  static constexpr int O_RTD = O_RY2 + NY;              // Rθdyn   NX×NTH  rθ0[dyn, :]
-  static constexpr int O_RTR = O_RTD + NX * NTH;        // Rθrst   NY×NTH  rθ0[rst, :]
-  static constexpr int O_CD = O_RTR + NY * NTH;         // cdyn    NX      rdyn0 − Dx x0 − Dy1 y10 − Rθdyn θ0
-  static constexpr int O_CR = O_CD + NX;                // crst    NY      rrst0 − Rx x0 − Ry1 y10 − Ry2∘y20 − Rθrst θ0
-  static constexpr int O_AI = O_CR + NY;                // Ai      NX×NX   Dx⁻¹                 (schur.jl:39)
-  static constexpr int O_CAI = O_AI + NX * NX;          // CAi     NY×NX   Rx Dx⁻¹              (schur.jl:40)
-  static constexpr int O_AIB = O_CAI + NY * NX;         // AiB     NX×NY   Dx⁻¹ Dy1
-  static constexpr int O_S0 = O_AIB + NX * NY;          // S0      NY×NY   Ry1 − Rx Dx⁻¹ Dy1    (schur.jl:41,85)
-  static constexpr int O_W = O_S0 + NY * NY;            // W       NY×NCOL CAi Rθdyn − Rθrst  (first NCOL columns)
-  static constexpr int O_AR = O_W + NY * NCOL;          // AR      NX×NCOL Ai Rθdyn           (first NCOL columns)
-  static constexpr int LIN_DOUBLES = O_AR + NX * NCOL;
-  static constexpr int LIN_STRIDE = round_up(LIN_DOUBLES, 16);  // 128 B multiples (bulk-copy friendly)
+  // ---- LinStore: per-knot constants, fp64, offsets in doubles --------------------------------
+  // Every lane-indexed matrix is padded to G rows and stored "lane fastest" so that the G lanes of a
+  // group read consecutive words (conflict-free LDS); pairs that are always consumed together are
+  // interleaved so that one 16-byte load feeds two FMAs.  Zero padding makes idle lanes harmless.
+  //
+  // Shared-memory part (copied per CTA by one cp.async.bulk when the knot changes):
+  static constexpr int O_RES = 0;                         // (NX+NY)×G×2  {[Dx Dy1][l][j], [Rx Ry1][l][j]}
+  static constexpr int O_CA2 = O_RES + (NX + NY) * G * 2;  // NX×G×2       {CAi[l][j], Ai[l][j]}
+  static constexpr int O_AIBC = O_CA2 + NX * G * 2;        // NY×G         AiB[l][j] at j*G + l
+  static constexpr int O_AIBR = O_AIBC + NY * G;           // NX×G         AiB[i][l] at i*G + l
+  static constexpr int O_S0 = O_AIBR + NX * G;             // NY×G         S0[l][j]  at j*G + l
+  static constexpr int O_S0T = O_S0 + NY * G;              // NY×G         S0[j][l]  at j*G + l
+  static constexpr int O_RY2 = O_S0T + NY * G;             // G            Ry2[l]
+  static constexpr int O_W = O_RY2 + G;                    // NCOL×NY      W[k][c]   at c*NY + k   (uniform reads)
+  static constexpr int O_AR = O_W + NCOL * NY;             // NCOL×G       AR[l][c]  at c*G + l
+  static constexpr int SMEM_DOUBLES = round_up(O_AR + NCOL * G, 2);
+  // Global-only part (touched once per subproblem, in the prologue; served by L1/L2):
+  static constexpr int O_C0 = SMEM_DOUBLES;                // G×2          {cdyn0[l], crst0[l]}
+  static constexpr int O_RTH = O_C0 + G * 2;               // NTH×G×2      {Rθdyn[l][j], Rθrst[l][j]}
+  static constexpr int LIN_DOUBLES = O_RTH + NTH * G * 2;
+  static constexpr int LIN_STRIDE = round_up(LIN_DOUBLES, 16);  // 128 B multiples
+  static_assert((SMEM_DOUBLES * 8) % 16 == 0, "bulk copy size must be a multiple of 16 B");
 };
 
 // The robots of BASELINE.json's configs (SURVEY.md §2 dimension table).

@@ -1,22 +1,30 @@
-// Batched Mehrotra predictor-corrector interior-point solve of the linearized contact subproblem.
+// Batched Mehrotra predictor-corrector interior-point solve of the linearized contact subproblem
+// (kernel v2: compact rolled loops, shared-memory exchange, TMA-staged per-knot constants).
 //
-// One group of G lanes (G = 4, 16 or 32; 32/G subproblems per warp) owns one subproblem: lane l
-// holds row l of every vector (x_l, y1_l, y2_l, residual rows) and row l of the ny×ny Schur
-// complement in registers.  Cross-row traffic is warp shuffles of width G.  Per-knot constants
-// (Dims::LinStore) are shared by every subproblem on the same reference knot and are read through
-// L1/L2.  Persistent grid-stride loop over the batch.
+// Mapping.  One group of G lanes (G = 4, 16 or 32; 32/G subproblems per warp) owns one subproblem;
+// lane l holds row l of every vector (x_l, y1_l, y2_l, residual rows) and row l of the ny×ny inverse of
+// the Schur complement in registers.  Vectors are exchanged between the rows of a group through a
+// small per-group shared-memory scratch (one STS per lane, 16-byte broadcast LDS on the way back),
+// scalars are reduced with width-G shuffles.  The per-knot constants (Dims::LinStore, ≈ 27 KB for the
+// quadruped) are shared by every subproblem on the same reference knot: each CTA stages them once
+// into shared memory with a single bulk-async copy (cp.async.bulk + mbarrier, the 1-D TMA path) and
+// re-stages only when its contiguous slice of the batch crosses into the next knot.  Warps pull
+// subproblem pairs from a CTA-local counter, so a slow subproblem only delays its own warp.
 //
 // Replaces, per subproblem (reference file:line):
 //   rlin!                         src/controller/linearized_solver.jl:364-373     -> residual()
-//   rzlin! + schur_factorize!     linearized_solver.jl:378-399, src/solver/schur.jl:80-88 -> factor()
-//   linear_solve!(Δ, rz, r)       linearized_solver.jl:424-444, schur.jl:93-110   -> lu_solve() + products
-//   linear_solve!(δz, rz, rθ)     linearized_solver.jl:451-479                    -> sensitivities
+//   rzlin! + schur_factorize!     linearized_solver.jl:378-399, src/solver/schur.jl:80-88 -> load_schur() + invert()
+//   linear_solve!(Δ, rz, r)       linearized_solver.jl:424-444, schur.jl:93-110   -> apply_inverse() + products
+//   linear_solve!(δz, rz, rθ)     linearized_solver.jl:451-479                    -> sensitivities()
 //   residual_/bilinear_violation  linearized_solver.jl:401-409                    -> group max-reductions
 //   general_correction_term!      linearized_solver.jl:411-418
 //   interior_point_solve!         RoboDojo 0.1.3 (external; iteration defined in oracle/ip.py)
-// The ny×ny system is factorised by LU with partial pivoting (rows stay in their lanes; the pivot
-// order is tracked) instead of the reference's modified Gram-Schmidt QR (src/solver/qr.jl:113-158):
-// same solution to fp64 round-off, one third of the flops, no column dot-products across lanes.
+// Linear algebra.  The reference re-factorises S = D − C A⁻¹ B (ny×ny) by modified Gram-Schmidt QR at
+// every iteration and back-substitutes (src/solver/qr.jl:113-158).  Here S is INVERTED in place by
+// Gauss-Jordan elimination with partial (row) pivoting — rows never leave their lanes, the pivot order
+// is tracked — so both solves of an iteration and all sensitivity right-hand sides become
+// matrix-vector / matrix-matrix products with no serial substitution chain.  Same solution to fp64
+// round-off (tests/test_gpu_parity.py), see DESIGN.md for the flop / latency argument.
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -43,6 +51,7 @@ struct IpParams {
 };
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int UNPIV = 1 << 20;
 
 // Guaranteed compile-time unrolling (register arrays must never be indexed dynamically).
 template <int B, int... Is, class F>
@@ -53,12 +62,7 @@ template <int B, int E, class F>
 __device__ __forceinline__ void static_for(F&& f) {
   if constexpr (E > B) static_for_impl<B>(std::make_integer_sequence<int, E - B>{}, static_cast<F&&>(f));
 }
-constexpr int UNPIV = 1 << 20;
 
-template <int G>
-__device__ __forceinline__ double bc(double v, int src) {
-  return __shfl_sync(FULL, v, src, G);
-}
 template <int G>
 __device__ __forceinline__ double gmax(double v) {
 #pragma unroll
@@ -78,109 +82,176 @@ __device__ __forceinline__ double gsum(double v) {
   return v;
 }
 
-// Per-lane LU state of the NY×NY Schur complement S = S0 − diag(Ry2 ŷ2 / ŷ1):
-// a[j] = row `l` of the factors (multipliers below the pivot order, U on and above it).
-template <int NY>
-struct LU {
-  double a[NY];
-  int piv[NY];  // lane (row) chosen as pivot of elimination step k — identical in all lanes
-  int mystep;   // elimination step at which this lane's row was the pivot row
-  int mypl;     // piv[l]: lane that holds unknown number l after back-substitution
-  double invp;  // 1 / (pivot element of this lane's row)
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+// ---- bulk-async (TMA 1-D) staging of one knot's constants ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Per-group shared-memory scratch (doubles).
+template <class D>
+struct GroupScratch {
+  static constexpr int NX = D::NX, NY = D::NY;
+  static constexpr int XYN = round_up(imax(NX + NY, D::NTH), 2);
+  static constexpr int O_XY = 0;                 // [x; y1] exchange (θ in the prologue, rdyn for the products)
+  static constexpr int O_WV = O_XY + XYN;        // RHS of a solve, permuted to pivot order
+  static constexpr int O_TV = O_WV + NY;         // solution of a solve, natural order
+  static constexpr int O_PROW = O_TV + NY;       // pivot row of a Gauss-Jordan step
+  static constexpr int O_SENS = O_PROW + NY;     // sensitivity workspace
+  static constexpr int LDP = NY + 1;             // padded leading dimension of lane-major scratch matrices
+  static constexpr int O_AIBP = O_SENS;          // NX×NY   AiB with columns permuted to pivot order
+  static constexpr int A_SZ = imax(NX * NY, D::MODE ? NY * LDP : 0);  // AiBp, later aliased by S⁻¹ rows
+  static constexpr int O_P1 = O_SENS + round_up(A_SZ, 2);    // NX×LDP  P1 = AiB S⁻¹
+  static constexpr int O_PL = O_P1 + round_up(NX * LDP, 2);  // NY ints: pivot lane of each step
+  static constexpr int DOUBLES = round_up(O_PL + (NY + 1) / 2, 2);
 };
 
 template <class D>
-__device__ __forceinline__ void factor(LU<D::NY>& f, int l, int gshift) {
-  constexpr int NY = D::NY, G = D::G;
-  f.mystep = UNPIV;
-  f.mypl = 0;
-  f.invp = 1.0;
-  static_for<0, NY>([&](auto K) {
-    constexpr int k = decltype(K)::value;
-    const bool unp = (f.mystep == UNPIV) && (l < NY);
-    const double cand = unp ? fabs(f.a[k]) : -1.0;
-    const double m = gmax<G>(cand);
-    unsigned bal = __ballot_sync(FULL, cand == m);
-    bal = (G == 32) ? bal : ((bal >> gshift) & ((1u << (G & 31)) - 1u));
-    const int p = __ffs(bal) - 1;
-    f.piv[k] = p;
-    if (l == k) f.mypl = p;
-    const double inv_own = 1.0 / f.a[k];
-    const double pinv = bc<G>(inv_own, p);
-    const bool is_p = (l == p);
-    if (is_p) {
-      f.mystep = k;
-      f.invp = inv_own;
-    }
-    const bool elim = unp && !is_p;
-    const double mult = f.a[k] * pinv;
-    if (elim) f.a[k] = mult;
-    static_for<k + 1, NY>([&](auto J) {
-      constexpr int j = decltype(J)::value;
-      const double pj = bc<G>(f.a[j], p);
-      if (elim) f.a[j] = fma(-mult, pj, f.a[j]);
-    });
-  });
-}
-
-// Solve S t = w for NR right-hand sides; on entry w[r] = row l of RHS r, on exit w[r] = t_l.
-template <class D, int NR>
-__device__ __forceinline__ void lu_solve(const LU<D::NY>& f, double (&w)[NR]) {
-  constexpr int NY = D::NY, G = D::G;
-  static_for<0, NY>([&](auto K) {  // forward: apply the row eliminations to the RHS
-    constexpr int k = decltype(K)::value;
-    const bool upd = f.mystep > k;
-    static_for<0, NR>([&](auto R) {
-      constexpr int r = decltype(R)::value;
-      const double wp = bc<G>(w[r], f.piv[k]);
-      if (upd) w[r] = fma(-f.a[k], wp, w[r]);
-    });
-  });
-  static_for<0, NY>([&](auto K) {  // backward: U t = c, unknown k lives in lane piv[k]
-    constexpr int k = NY - 1 - decltype(K)::value;
-    const bool upd = f.mystep < k;
-    const bool mine = f.mystep == k;
-    static_for<0, NR>([&](auto R) {
-      constexpr int r = decltype(R)::value;
-      const double tk = bc<G>(w[r] * f.invp, f.piv[k]);
-      if (upd) w[r] = fma(-f.a[k], tk, w[r]);
-      if (mine) w[r] = tk;
-    });
-  });
-  static_for<0, NR>([&](auto R) {
-    constexpr int r = decltype(R)::value;
-    w[r] = bc<G>(w[r], f.mypl);  // unknown l → lane l
-  });
-}
+struct Ctx {  // per-lane registers of one subproblem
+  double x, y1, y2;
+  double cdyn, crst, ry2;
+  double rdyn, rrst, rbil;
+  double M[D::NY];  // row of P·S⁻¹ in pivot-order column slots
+  int mystep;       // Gauss-Jordan step at which this lane's row was the pivot row
+};
 
 // rlin!: rows of [rdyn; rrst; rbil] at (x, y1, y2) with central-path parameter kappa.
 template <class D>
-__device__ __forceinline__ void residual(const double* __restrict__ L, int lx, int ly, bool hx, bool hy,
-                                         double cdyn, double crst, double ry2, double x, double y1,
-                                         double y2, double kappa, double& rdyn, double& rrst,
-                                         double& rbil) {
+__device__ __forceinline__ void residual(const double* __restrict__ Ls, double* __restrict__ sc, int l, bool hx,
+                                         bool hy, double cdyn, double crst, double ry2, double x, double y1,
+                                         double y2, double kappa, double& rdyn, double& rrst, double& rbil) {
   constexpr int NX = D::NX, NY = D::NY, G = D::G;
+  using S = GroupScratch<D>;
+  if (hx) sc[S::O_XY + l] = x;
+  if (hy) sc[S::O_XY + NX + l] = y1;
+  __syncwarp();
   double ad = cdyn, ar = fma(ry2, y2, crst);
-#pragma unroll
-  for (int j = 0; j < NX; ++j) {
-    const double xb = bc<G>(x, j);
-    ad = fma(__ldg(L + D::O_DX + lx + j * NX), xb, ad);
-    ar = fma(__ldg(L + D::O_RX + ly + j * NY), xb, ar);
+  const double* R = Ls + D::O_RES + 2 * l;
+  constexpr int NJ = NX + NY;
+#pragma unroll 2
+  for (int j = 0; j + 1 < NJ; j += 2) {
+    const double2 v = lds2(sc + S::O_XY + j);
+    const double2 c0 = lds2(R + (j)*G * 2), c1 = lds2(R + (j + 1) * G * 2);
+    ad = fma(c0.x, v.x, ad);
+    ar = fma(c0.y, v.x, ar);
+    ad = fma(c1.x, v.y, ad);
+    ar = fma(c1.y, v.y, ar);
   }
-#pragma unroll
-  for (int j = 0; j < NY; ++j) {
-    const double yb = bc<G>(y1, j);
-    ad = fma(__ldg(L + D::O_DY1 + lx + j * NX), yb, ad);
-    ar = fma(__ldg(L + D::O_RY1 + ly + j * NY), yb, ar);
+  if constexpr (NJ & 1) {
+    const double v = sc[S::O_XY + NJ - 1];
+    const double2 c0 = lds2(R + (NJ - 1) * G * 2);
+    ad = fma(c0.x, v, ad);
+    ar = fma(c0.y, v, ar);
   }
+  __syncwarp();
   rdyn = hx ? ad : 0.0;
   rrst = hy ? ar : 0.0;
   rbil = hy ? fma(y1, y2, -kappa) : 0.0;
 }
 
+// In-place Gauss-Jordan inversion with partial pivoting of the matrix whose row l is c.M[] (lane l).
+// Columns are processed four at a time with static register indices, then the row is rotated by four
+// so that the loop body is the same code for every block (compact, I-cache resident).
+// On exit lane l = p_k (the pivot lane of step k = c.mystep) holds row k of (QA)⁻¹ = A⁻¹Qᵀ:
+//   c.M[j] = A⁻¹[mystep][p_j].
+template <class D, bool RECORD_PL>
+__device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l, int gshift, bool hy) {
+  constexpr int NY = D::NY, G = D::G;
+  using S = GroupScratch<D>;
+  c.mystep = UNPIV;
+  int* pl = reinterpret_cast<int*>(sc + S::O_PL);
+#pragma unroll 1
+  for (int kb = 0; kb < NY; kb += 4) {
+    static_for<0, 4>([&](auto U) {
+      constexpr int u = decltype(U)::value;
+      const bool unp = (c.mystep == UNPIV) && hy;
+      const double cand = unp ? fabs(c.M[u]) : -1.0;
+      const double m = gmax<G>(cand);
+      unsigned bal = __ballot_sync(FULL, cand == m);
+      bal = (G == 32) ? bal : ((bal >> gshift) & ((1u << (G & 31)) - 1u));
+      const int p = __ffs(bal) - 1;
+      const bool is_p = (l == p);
+      if (is_p) {
+        c.mystep = kb + u;
+        if (RECORD_PL) pl[kb + u] = l;
+        static_for<0, NY / 2>([&](auto J) {
+          constexpr int j = decltype(J)::value;
+          *reinterpret_cast<double2*>(sc + S::O_PROW + 2 * j) = make_double2(c.M[2 * j], c.M[2 * j + 1]);
+        });
+      }
+      __syncwarp();
+      const double pinv = __drcp_rn(sc[S::O_PROW + u]);
+      const double f = c.M[u];
+      const double g = is_p ? pinv : -f * pinv;  // new entry of the pivot column, and update factor
+      static_for<0, NY / 2>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const double2 pr = lds2(sc + S::O_PROW + 2 * j);
+        if constexpr (2 * j != u) c.M[2 * j] = is_p ? pr.x * pinv : fma(g, pr.x, c.M[2 * j]);
+        if constexpr (2 * j + 1 != u) c.M[2 * j + 1] = is_p ? pr.y * pinv : fma(g, pr.y, c.M[2 * j + 1]);
+      });
+      c.M[u] = g;
+      __syncwarp();
+    });
+    // rotate the row left by four column slots
+    const double t0 = c.M[0], t1 = c.M[1], t2 = c.M[2], t3 = c.M[3];
+    static_for<0, NY - 4>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      c.M[j] = c.M[j + 4];
+    });
+    c.M[NY - 4] = t0;
+    c.M[NY - 3] = t1;
+    c.M[NY - 2] = t2;
+    c.M[NY - 1] = t3;
+  }
+}
+
+// t = S⁻¹ w with the inverse held as c.M: w is scattered to pivot order, every lane forms its dot
+// product, the result is scattered back to natural order.  Returns t_l; sc[O_TV + j] = t_j for all j.
 template <class D>
-__device__ __forceinline__ double step_length(bool hy, double y1, double y2, double d1, double d2,
-                                              double tau) {
+__device__ __forceinline__ double apply_inverse(const Ctx<D>& c, double* __restrict__ sc, int l, bool hy, double w) {
+  constexpr int NY = D::NY;
+  using S = GroupScratch<D>;
+  if (hy) sc[S::O_WV + c.mystep] = w;
+  __syncwarp();
+  double a0 = 0.0, a1 = 0.0;
+  static_for<0, NY / 2>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const double2 v = lds2(sc + S::O_WV + 2 * j);
+    a0 = fma(c.M[2 * j], v.x, a0);
+    a1 = fma(c.M[2 * j + 1], v.y, a1);
+  });
+  if (hy) sc[S::O_TV + c.mystep] = a0 + a1;
+  __syncwarp();
+  return hy ? sc[S::O_TV + l] : 0.0;
+}
+
+template <class D>
+__device__ __forceinline__ double step_length(bool hy, double y1, double y2, double d1, double d2, double tau) {
   // largest α ≤ 1 with y − αΔ ≥ (1−τ) y on the orthant (fraction to the boundary)
   double a = 1.0;
   if (hy && d1 > 0.0) a = fmin(a, tau * y1 / d1);
@@ -188,188 +259,313 @@ __device__ __forceinline__ double step_length(bool hy, double y1, double y2, dou
   return gmin<D::G>(a);
 }
 
+// rzlin!: row l of S (or of Sᵀ) = S0 − diag(Ry2 ŷ2 / ŷ1).
+template <class D, bool TRANSPOSED>
+__device__ __forceinline__ void load_schur(Ctx<D>& c, const double* __restrict__ Ls, int l, bool hy, double reg) {
+  constexpr int NY = D::NY, G = D::G;
+  const double y1r = fmax(c.y1, reg), y2r = fmax(c.y2, reg);
+  const double dd = c.ry2 * y2r / y1r;
+  const double* S0 = Ls + (TRANSPOSED ? D::O_S0T : D::O_S0) + l;
+  static_for<0, NY>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    const double s0 = S0[j * G];
+    c.M[j] = hy ? ((j == l) ? s0 - dd : s0) : 0.0;
+  });
+}
+
+// differentiate_solution! restricted to the rows / columns Newton consumes:
+//   δx  = −(AR + AiB S⁻¹ W)          rows 1:nx      (δq0, δq1, δu1 blocks of q2)
+//   δy1 =  S⁻¹ W                      rows nx+1:nd   (γ1, b1; :configurationforce only)
+// with W = CAi Rθdyn − Rθrst and AR = Ai Rθdyn precomputed per knot.  Sᵀ is inverted so that lane q_k
+// holds COLUMN k of S⁻¹; P1 = AiB S⁻¹ then needs no cross-lane sums, and the final products run with
+// lane = output row and broadcast (uniform-address) loads of W.
+template <class D>
+__device__ __forceinline__ void sensitivities(Ctx<D>& c, const double* __restrict__ Ls, double* __restrict__ sc, int l,
+                                              int gshift, bool hx, bool hy, double reg, double* __restrict__ dzo,
+                                              bool valid) {
+  constexpr int NX = D::NX, NY = D::NY, G = D::G, NCOL = D::NCOL, ND = D::ND, NYD = D::NYD;
+  using S = GroupScratch<D>;
+  load_schur<D, true>(c, Ls, l, hy, reg);
+  invert<D, (NYD > 0)>(c, sc, l, gshift, hy);  // c.M[j] = S⁻¹[q_j][k],  k = c.mystep, lane = q_k
+  // AiBp[i][m] = AiB[i][q_m]: lane l = q_m owns column l of AiB
+  if (hy) {
+#pragma unroll 1
+    for (int i = 0; i < NX; ++i) sc[S::O_AIBP + i * NY + c.mystep] = Ls[D::O_AIBR + i * G + l];
+  }
+  __syncwarp();
+  // P1[i][k] = Σ_m AiBp[i][m] · S⁻¹[q_m][k]
+#pragma unroll 1
+  for (int i = 0; i < NX; ++i) {
+    double a0 = 0.0, a1 = 0.0;
+    static_for<0, NY / 2>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const double2 v = lds2(sc + S::O_AIBP + i * NY + 2 * j);
+      a0 = fma(c.M[2 * j], v.x, a0);
+      a1 = fma(c.M[2 * j + 1], v.y, a1);
+    });
+    if (hy) sc[S::O_P1 + i * S::LDP + c.mystep] = a0 + a1;
+  }
+  __syncwarp();
+  double Ar[NYD > 0 ? NY : 1];
+  if constexpr (NYD > 0) {
+    // rows of S⁻¹ for the force rows: Ainv[r][k] = S⁻¹[r][k], scattered from the column-held inverse
+    const int* pl = reinterpret_cast<const int*>(sc + S::O_PL);
+    if (hy) {
+      static_for<0, NY>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        sc[S::O_AIBP + pl[j] * S::LDP + c.mystep] = c.M[j];
+      });
+    }
+    __syncwarp();
+    static_for<0, NY>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      Ar[j] = (l < NYD) ? sc[S::O_AIBP + l * S::LDP + j] : 0.0;
+    });
+  }
+  // row l of P1 (c.M is dead: reuse its registers)
+  static_for<0, NY>([&](auto J) {
+    constexpr int j = decltype(J)::value;
+    c.M[j] = hx ? sc[S::O_P1 + l * S::LDP + j] : 0.0;
+  });
+  __syncwarp();
+#pragma unroll 1
+  for (int col = 0; col < NCOL; ++col) {
+    const double* Wc = Ls + D::O_W + col * NY;
+    double a0 = Ls[D::O_AR + col * G + l], a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    static_for<0, NY / 2>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const double2 w = lds2(Wc + 2 * j);
+      a0 = fma(c.M[2 * j], w.x, a0);
+      a1 = fma(c.M[2 * j + 1], w.y, a1);
+      if constexpr (NYD > 0) {
+        b0 = fma(Ar[2 * j], w.x, b0);
+        b1 = fma(Ar[2 * j + 1], w.y, b1);
+      }
+    });
+    if (valid) {
+      if (hx) dzo[col * ND + l] = -(a0 + a1);
+      if constexpr (NYD > 0) {
+        if (l < NYD) dzo[col * ND + NX + l] = b0 + b1;
+      }
+    }
+  }
+}
+
+template <class D, int THREADS>
+struct KernelSmem {
+  static constexpr int GROUPS = THREADS / D::G;
+  static constexpr int GS = round_up(GroupScratch<D>::DOUBLES, 2);
+  static constexpr size_t BYTES = (size_t)(D::SMEM_DOUBLES + GROUPS * GS) * 8 + 64;
+};
+
 template <class D, int THREADS>
 __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
-  constexpr int NX = D::NX, NY = D::NY, NTH = D::NTH, NCOL = D::NCOL, NZ = D::NZ, NC = D::NC;
+  constexpr int NX = D::NX, NY = D::NY, NTH = D::NTH, NZ = D::NZ, NC = D::NC;
   constexpr int G = D::G, PPW = 32 / G;
-  constexpr int NTHR = (NTH + G - 1) / G;
+  using S = GroupScratch<D>;
+  using KS = KernelSmem<D, THREADS>;
 
-  const int lane = threadIdx.x & 31;
-  const int l = lane % G;
-  const int gi = lane / G;
-  const int gshift = gi * G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Ls = reinterpret_cast<double*>(smem_raw);                      // staged knot constants
+  double* scratch = Ls + D::SMEM_DOUBLES;                                // per-group scratch
+  uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + KS::GROUPS * KS::GS);
+  int* ctl = reinterpret_cast<int*>(bar + 1);  // [0] next subproblem of the segment, [1] segment end, [2] knot
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int l = lane % G, gi = lane / G, gshift = gi * G;
   const bool hx = l < NX, hy = l < NY;
-  const int lx = hx ? l : 0, ly = hy ? l : 0;
-  const int64_t warp0 = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * (THREADS / 32);
+  double* sc = scratch + (size_t)(tid / G) * KS::GS;
   const cimpc_ip_opts o = p.o;
 
-  for (int64_t wb = warp0 * PPW; wb < p.n; wb += nwarps * PPW) {
-    const int64_t prob = wb + gi;
-    const bool valid = prob < p.n;
-    const int64_t pi = valid ? prob : wb;  // idle groups shadow the warp's first problem
-    int kn = p.knot[pi];
-    kn = (kn < 0 || kn >= p.h_ref) ? 0 : kn;  // range is validated by the host entry point
-    const double* __restrict__ L = p.lin + (int64_t)kn * D::LIN_STRIDE;
+  // this CTA's contiguous slice of the batch
+  const int64_t c0 = p.n * (int64_t)blockIdx.x / gridDim.x, c1 = p.n * (int64_t)(blockIdx.x + 1) / gridDim.x;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  int staged = -1;
+  uint32_t phase = 0;
 
-    // ---- prologue: θ-dependent constants  c = c0 + Rθ θ (+ alt on the impact rows) ----
-    double th[NTHR];
-#pragma unroll
-    for (int r = 0; r < NTHR; ++r) {
-      const int j = l + r * G;
-      th[r] = (j < NTH) ? p.theta[pi * NTH + j] : 0.0;
+  for (int64_t cur = c0; cur < c1;) {
+    // ---- segment = maximal run of subproblems on the same reference knot ----
+    if (tid == 0) {
+      const int kn0 = p.knot[cur];
+      ctl[2] = (kn0 < 0 || kn0 >= p.h_ref) ? 0 : kn0;  // range is validated by the host entry point
+      ctl[1] = (int)(c1 - c0);
+      ctl[0] = 0;
     }
-    double cdyn = __ldg(L + D::O_CD + lx), crst = __ldg(L + D::O_CR + ly);
-#pragma unroll
-    for (int j = 0; j < NTH; ++j) {
-      const double tb = bc<G>(th[j / G], j % G);
-      cdyn = fma(__ldg(L + D::O_RTD + lx + j * NX), tb, cdyn);
-      crst = fma(__ldg(L + D::O_RTR + ly + j * NY), tb, crst);
+    __syncthreads();
+    const int kn = ctl[2];
+    const int kraw = p.knot[cur];
+    for (int64_t i = cur + 1 + tid; i < c1; i += THREADS)
+      if (p.knot[i] != kraw) {
+        atomicMin(&ctl[1], (int)(i - c0));
+        break;
+      }
+    __syncthreads();
+    const int64_t seg_end = c0 + ctl[1];
+    if (kn != staged) {  // CTA-uniform
+      if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)(D::SMEM_DOUBLES * 8));
+        bulk_g2s(Ls, p.lin + (int64_t)kn * D::LIN_STRIDE, (uint32_t)(D::SMEM_DOUBLES * 8), bar);
+      }
+      while (!mbar_try_wait(bar, phase)) {
+      }
+      phase ^= 1u;
+      staged = kn;
     }
-    if (p.alt != nullptr && l < NC) crst += p.alt[pi * NC + l];
-    const double ry2 = hy ? __ldg(L + D::O_RY2 + ly) : 0.0;
+    const double* __restrict__ Lg = p.lin + (int64_t)kn * D::LIN_STRIDE;  // global-only part (prologue)
 
-    // ---- cold start: z = 1, z[q2] = q2_init  (z_initialize!) ----
-    double x = hx ? p.q2_init[pi * NX + lx] : 0.0;
-    double y1 = 1.0, y2 = 1.0;
-    double rdyn, rrst, rbil;
-    residual<D>(L, lx, ly, hx, hy, cdyn, crst, ry2, x, y1, y2, 0.0, rdyn, rrst, rbil);
-    double r_vio = gmax<G>(fmax(fabs(rdyn), fabs(rrst)));
-    double k_vio = gmax<G>(fabs(rbil));
+    // ---- warps pull PPW subproblems at a time from the segment ----
+    for (;;) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&ctl[0], PPW);
+      base = __shfl_sync(FULL, base, 0);
+      const int64_t wb = cur + base;
+      if (wb >= seg_end) break;
+      const int64_t prob = wb + gi;
+      const bool valid = prob < seg_end;
+      const int64_t pi = valid ? prob : wb;  // idle groups shadow the warp's first subproblem
 
-    bool done = !valid;
-    int iters = 0;
-    double reg = 0.0;
-    LU<NY> f;
-
-    for (int it = 0; it < o.max_iter; ++it) {
-      if (r_vio < o.r_tol && k_vio < o.kappa_tol) done = true;
-      if (__all_sync(FULL, done)) break;
-
-      const double reg_it = (k_vio < o.kappa_reg) ? k_vio * o.gamma_reg : 0.0;
-      const double y1r = fmax(y1, reg_it), y2r = fmax(y2, reg_it);
-      // rzlin!: S = (Ry1 − Rx Dx⁻¹ Dy1) − diag(Ry2 ŷ2 / ŷ1), then factorise
-      const double dd = ry2 * y2r / y1r;
-#pragma unroll
-      for (int j = 0; j < NY; ++j) {
-        const double s0 = hy ? __ldg(L + D::O_S0 + ly + j * NY) : 0.0;
-        f.a[j] = (j == l) ? s0 - dd : s0;
-      }
-      factor<D>(f, l, gshift);
-
-      // constant products with u = rdyn (shared by predictor and corrector)
-      double cu = 0.0, au = 0.0;
-#pragma unroll
-      for (int j = 0; j < NX; ++j) {
-        const double ub = bc<G>(rdyn, j);
-        cu = fma(__ldg(L + D::O_CAI + ly + j * NY), ub, cu);
-        au = fma(__ldg(L + D::O_AI + lx + j * NX), ub, au);
-      }
-
-      // ---- predictor (affine) direction: only Δy1, Δy2 are needed ----
-      double w[1];
-      w[0] = hy ? cu - (rrst - ry2 * rbil / y1r) : 0.0;
-      lu_solve<D, 1>(f, w);
-      const double dy1a = -w[0];
-      const double dy2a = hy ? (rbil - y2r * dy1a) / y1r : 0.0;
-      const double a_aff = step_length<D>(hy, y1, y2, dy1a, dy2a, 1.0);
-      const double mu = gsum<G>(hy ? y1 * y2 : 0.0) / (double)NY;
-      const double mu_aff =
-          gsum<G>(hy ? (y1 - a_aff * dy1a) * (y2 - a_aff * dy2a) : 0.0) / (double)NY;
-      double sg = fmin(fmax(mu_aff / mu, 0.0), 1.0);
-      sg = sg * sg * sg;
-      const double kap = fmax(sg * mu, o.kappa_tol / o.undercut);
-
-      // ---- corrector: rbil = y1∘y2 − κ + Δy1aff∘Δy2aff ----
-      const double rbc = hy ? fma(y1, y2, -kap) + dy1a * dy2a : 0.0;
-      w[0] = hy ? cu - (rrst - ry2 * rbc / y1r) : 0.0;
-      lu_solve<D, 1>(f, w);
-      const double t = w[0];
-      const double dy1 = -t;
-      const double dy2 = hy ? (rbc - y2r * dy1) / y1r : 0.0;
-      double dx = au;
-#pragma unroll
-      for (int j = 0; j < NY; ++j) dx = fma(__ldg(L + D::O_AIB + lx + j * NX), bc<G>(t, j), dx);
-      if (!hx) dx = 0.0;
-
-      const double vmax = fmax(r_vio, k_vio);
-      const double tau = fmax(1.0 - o.eps_min, 1.0 - vmax * vmax);
-      double alpha = step_length<D>(hy, y1, y2, dy1, dy2, tau);
-
-      // ---- candidate + back-tracking on the violations (trial max_ls is accepted unconditionally) ----
-      bool acc = done;
-      double xc = x, y1c = y1, y2c = y2, rdc = rdyn, rrc = rrst, rbc2 = rbil, rvc = r_vio, kvc = k_vio;
-      for (int ls = 0; ls <= o.max_ls; ++ls) {
-        const double xt = x - alpha * dx, y1t = y1 - alpha * dy1, y2t = y2 - alpha * dy2;
-        double rd, rr, rb;
-        residual<D>(L, lx, ly, hx, hy, cdyn, crst, ry2, xt, y1t, y2t, 0.0, rd, rr, rb);
-        const double rv = gmax<G>(fmax(fabs(rd), fabs(rr)));
-        const double kv = gmax<G>(fabs(rb));
-        if (!acc) {
-          xc = xt; y1c = y1t; y2c = y2t; rdc = rd; rrc = rr; rbc2 = rb; rvc = rv; kvc = kv;
-          if (rv <= r_vio || kv <= k_vio || ls == o.max_ls) acc = true;
-          else alpha *= o.ls_scale;
+      Ctx<D> c;
+      // prologue: θ-dependent constants  c = c0 + Rθ θ (+ alt on the impact rows)
+#pragma unroll 1
+      for (int j = l; j < NTH; j += G) sc[S::O_XY + j] = p.theta[pi * NTH + j];
+      __syncwarp();
+      {
+        const double2 c00 = __ldg(reinterpret_cast<const double2*>(Lg + D::O_C0) + l);
+        double cd = c00.x, cr = c00.y;
+        const double2* R = reinterpret_cast<const double2*>(Lg + D::O_RTH) + l;
+#pragma unroll 2
+        for (int j = 0; j < NTH; ++j) {
+          const double2 r = __ldg(R + j * G);
+          const double t = sc[S::O_XY + j];
+          cd = fma(r.x, t, cd);
+          cr = fma(r.y, t, cr);
         }
-        if (__all_sync(FULL, acc)) break;
+        if (p.alt != nullptr && l < NC) cr += p.alt[pi * NC + l];
+        c.cdyn = cd;
+        c.crst = cr;
       }
-      if (!done) {
-        x = xc; y1 = y1c; y2 = y2c; rdyn = rdc; rrst = rrc; rbil = rbc2; r_vio = rvc; k_vio = kvc;
-        reg = reg_it;
-        ++iters;
-      }
-    }
-    const bool conv = (r_vio < o.r_tol) && (k_vio < o.kappa_tol);
+      __syncwarp();
+      c.ry2 = Ls[D::O_RY2 + l];
+      // cold start: z = 1, z[q2] = q2_init  (z_initialize!)
+      c.x = hx ? p.q2_init[pi * NX + l] : 0.0;
+      c.y1 = 1.0;
+      c.y2 = 1.0;
+      residual<D>(Ls, sc, l, hx, hy, c.cdyn, c.crst, c.ry2, c.x, c.y1, c.y2, 0.0, c.rdyn, c.rrst, c.rbil);
+      double r_vio = gmax<G>(fmax(fabs(c.rdyn), fabs(c.rrst)));
+      double k_vio = gmax<G>(fabs(c.rbil));
 
-    // ---- outputs: z*, status, iteration count ----
-    if (valid) {
-      double* zo = p.z_out + prob * NZ;
-      if (hx) zo[l] = x;
-      if (hy) {
-        zo[NX + l] = y1;
-        zo[NX + NY + l] = y2;
-      }
-      if (l == 0) {
-        p.status[prob] = conv ? 1 : 0;
-        p.iters[prob] = iters;
-      }
-    }
+      bool done = !valid;
+      int iters = 0;
+      double reg = 0.0;
 
-    // ---- differentiate_solution!: δz = −rz⁻¹ rθ on the consumed rows / columns ----
-    if (o.diff_sol) {
-      const double reg_d = fmax(reg, o.kappa_tol * o.gamma_reg);
-      const double y1r = fmax(y1, reg_d), y2r = fmax(y2, reg_d);
-      const double dd = ry2 * y2r / y1r;
-#pragma unroll
-      for (int j = 0; j < NY; ++j) {
-        const double s0 = hy ? __ldg(L + D::O_S0 + ly + j * NY) : 0.0;
-        f.a[j] = (j == l) ? s0 - dd : s0;
-      }
-      factor<D>(f, l, gshift);
-      constexpr int CH = (NCOL % 6 == 0) ? 6 : ((NCOL % 5 == 0) ? 5 : 1);
-      double* dzo = p.dz_out + prob * (int64_t)(D::ND * NCOL);
-      for (int c0 = 0; c0 < NCOL; c0 += CH) {
-        double w[CH];
-#pragma unroll
-        for (int r = 0; r < CH; ++r) w[r] = hy ? __ldg(L + D::O_W + ly + (c0 + r) * NY) : 0.0;
-        lu_solve<D, CH>(f, w);  // w = S⁻¹ (CAi Rθdyn − Rθrst)[:, c] = −δy1
-        double dxo[CH];
-#pragma unroll
-        for (int r = 0; r < CH; ++r) dxo[r] = __ldg(L + D::O_AR + lx + (c0 + r) * NX);
-#pragma unroll
-        for (int j = 0; j < NY; ++j) {
-          const double m = __ldg(L + D::O_AIB + lx + j * NX);
-#pragma unroll
-          for (int r = 0; r < CH; ++r) dxo[r] = fma(m, bc<G>(w[r], j), dxo[r]);
-        }
-        if (valid) {
-#pragma unroll
-          for (int r = 0; r < CH; ++r) {
-            if (hx) dzo[(c0 + r) * D::ND + l] = -dxo[r];
-            if (D::NYD > 0 && l < D::NYD) dzo[(c0 + r) * D::ND + NX + l] = w[r];
+#pragma unroll 1
+      for (int it = 0; it < o.max_iter; ++it) {
+        if (r_vio < o.r_tol && k_vio < o.kappa_tol) done = true;
+        if (!(r_vio == r_vio) || !(k_vio == k_vio)) done = true;  // NaN (singular pivot): give up, status 0
+        if (__all_sync(FULL, done)) break;
+
+        const double reg_it = (k_vio < o.kappa_reg) ? k_vio * o.gamma_reg : 0.0;
+        const double y1r = fmax(c.y1, reg_it), y2r = fmax(c.y2, reg_it);
+        // rzlin! + schur_factorize!  →  S⁻¹
+        load_schur<D, false>(c, Ls, l, hy, reg_it);
+        invert<D, false>(c, sc, l, gshift, hy);
+
+        // constant products with u = rdyn (shared by predictor and corrector): cu = CAi u, au = Ai u
+        double cu = 0.0, au = 0.0;
+        if (hx) sc[S::O_XY + l] = c.rdyn;
+        __syncwarp();
+        {
+          const double* CA = Ls + D::O_CA2 + 2 * l;
+#pragma unroll 1
+          for (int j = 0; j < NX; ++j) {
+            const double2 k2 = lds2(CA + j * G * 2);
+            const double ub = sc[S::O_XY + j];
+            cu = fma(k2.x, ub, cu);
+            au = fma(k2.y, ub, au);
           }
         }
+        __syncwarp();
+
+        // ---- predictor (affine) direction: only Δy1, Δy2 are needed ----
+        double t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * c.rbil / y1r) : 0.0);
+        const double dy1a = -t;
+        const double dy2a = hy ? (c.rbil - y2r * dy1a) / y1r : 0.0;
+        const double a_aff = step_length<D>(hy, c.y1, c.y2, dy1a, dy2a, 1.0);
+        const double mu = gsum<G>(hy ? c.y1 * c.y2 : 0.0) / (double)NY;
+        const double mu_aff = gsum<G>(hy ? (c.y1 - a_aff * dy1a) * (c.y2 - a_aff * dy2a) : 0.0) / (double)NY;
+        double sg = fmin(fmax(mu_aff / mu, 0.0), 1.0);
+        sg = sg * sg * sg;
+        const double kap = fmax(sg * mu, o.kappa_tol / o.undercut);
+
+        // ---- corrector: rbil = y1∘y2 − κ + Δy1aff∘Δy2aff ----
+        const double rbc = hy ? fma(c.y1, c.y2, -kap) + dy1a * dy2a : 0.0;
+        t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * rbc / y1r) : 0.0);
+        const double dy1 = -t;
+        const double dy2 = hy ? (rbc - y2r * dy1) / y1r : 0.0;
+        double dx = au;
+        {
+          const double* AB = Ls + D::O_AIBC + l;
+#pragma unroll 2
+          for (int j = 0; j < NY; j += 2) {
+            const double2 tv = lds2(sc + S::O_TV + j);
+            dx = fma(AB[j * G], tv.x, dx);
+            dx = fma(AB[(j + 1) * G], tv.y, dx);
+          }
+        }
+        if (!hx) dx = 0.0;
+
+        const double vmax = fmax(r_vio, k_vio);
+        const double tau = fmax(1.0 - o.eps_min, 1.0 - vmax * vmax);
+        double alpha = step_length<D>(hy, c.y1, c.y2, dy1, dy2, tau);
+
+        // ---- candidate + back-tracking on the violations (trial max_ls is accepted unconditionally) ----
+        bool acc = done;
+        double xc = c.x, y1c = c.y1, y2c = c.y2, rdc = c.rdyn, rrc = c.rrst, rbc2 = c.rbil, rvc = r_vio, kvc = k_vio;
+#pragma unroll 1
+        for (int ls = 0; ls <= o.max_ls; ++ls) {
+          const double xt = c.x - alpha * dx, y1t = c.y1 - alpha * dy1, y2t = c.y2 - alpha * dy2;
+          double rd, rr, rb;
+          residual<D>(Ls, sc, l, hx, hy, c.cdyn, c.crst, c.ry2, xt, y1t, y2t, 0.0, rd, rr, rb);
+          const double rv = gmax<G>(fmax(fabs(rd), fabs(rr)));
+          const double kv = gmax<G>(fabs(rb));
+          if (!acc) {
+            xc = xt; y1c = y1t; y2c = y2t; rdc = rd; rrc = rr; rbc2 = rb; rvc = rv; kvc = kv;
+            if (rv <= r_vio || kv <= k_vio || ls == o.max_ls) acc = true;
+            else alpha *= o.ls_scale;
+          }
+          if (__all_sync(FULL, acc)) break;
+        }
+        if (!done) {
+          c.x = xc; c.y1 = y1c; c.y2 = y2c; c.rdyn = rdc; c.rrst = rrc; c.rbil = rbc2; r_vio = rvc; k_vio = kvc;
+          reg = reg_it;
+          ++iters;
+        }
       }
+      const bool conv = (r_vio < o.r_tol) && (k_vio < o.kappa_tol);
+
+      // ---- outputs: z*, status, iteration count ----
+      if (valid) {
+        double* zo = p.z_out + prob * NZ;
+        if (hx) zo[l] = c.x;
+        if (hy) {
+          zo[NX + l] = c.y1;
+          zo[NX + NY + l] = c.y2;
+        }
+        if (l == 0) {
+          p.status[prob] = conv ? 1 : 0;
+          p.iters[prob] = iters;
+        }
+      }
+      // ---- differentiate_solution! ----
+      if (o.diff_sol) {
+        const double reg_d = fmax(reg, o.kappa_tol * o.gamma_reg);
+        sensitivities<D>(c, Ls, sc, l, gshift, hx, hy, reg_d, p.dz_out + prob * (int64_t)(D::ND * D::NCOL), valid);
+      }
+      __syncwarp();
     }
+    __syncthreads();  // every warp is done with this segment (and with Ls) before the next one is staged
+    cur = seg_end;
   }
 }
 

@@ -6,10 +6,10 @@
 
 namespace cimpc {
 
-struct LinLayout {  // runtime copy of Dims<...>::O_* (doubles)
+struct LinLayout {  // runtime copy of Dims<...> (offsets in doubles)
   int nx, ny, nz, nth, ncol, nd, group;
-  int o_dx, o_dy1, o_rx, o_ry1, o_ry2, o_rtd, o_rtr, o_cd, o_cr, o_ai, o_cai, o_aib, o_s0, o_w, o_ar;
-  int stride;
+  int o_res, o_ca2, o_aibc, o_aibr, o_s0, o_s0t, o_ry2, o_w, o_ar, o_c0, o_rth;
+  int smem_doubles, stride;
 };
 
 struct ModelEntry {
@@ -20,38 +20,49 @@ struct ModelEntry {
   cudaError_t (*occupancy)(int* blocks_per_sm);
 };
 
-constexpr int IP_THREADS = 128;
+constexpr int IP_THREADS = 256;
 
 template <class D>
 LinLayout layout_of() {
   LinLayout l;
   l.nx = D::NX; l.ny = D::NY; l.nz = D::NZ; l.nth = D::NTH; l.ncol = D::NCOL; l.nd = D::ND; l.group = D::G;
-  l.o_dx = D::O_DX; l.o_dy1 = D::O_DY1; l.o_rx = D::O_RX; l.o_ry1 = D::O_RY1; l.o_ry2 = D::O_RY2;
-  l.o_rtd = D::O_RTD; l.o_rtr = D::O_RTR; l.o_cd = D::O_CD; l.o_cr = D::O_CR; l.o_ai = D::O_AI;
-  l.o_cai = D::O_CAI; l.o_aib = D::O_AIB; l.o_s0 = D::O_S0; l.o_w = D::O_W; l.o_ar = D::O_AR;
-  l.stride = D::LIN_STRIDE;
+  l.o_res = D::O_RES; l.o_ca2 = D::O_CA2; l.o_aibc = D::O_AIBC; l.o_aibr = D::O_AIBR; l.o_s0 = D::O_S0;
+  l.o_s0t = D::O_S0T; l.o_ry2 = D::O_RY2; l.o_w = D::O_W; l.o_ar = D::O_AR; l.o_c0 = D::O_C0; l.o_rth = D::O_RTH;
+  l.smem_doubles = D::SMEM_DOUBLES; l.stride = D::LIN_STRIDE;
   return l;
 }
 
 template <class D>
+cudaError_t prepare_ip() {  // opt in to > 48 KB of dynamic shared memory (once per instance)
+  static cudaError_t once = cudaFuncSetAttribute(ip_solve_kernel<D, IP_THREADS>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)KernelSmem<D, IP_THREADS>::BYTES);
+  return once;
+}
+
+template <class D>
 cudaError_t occupancy_ip(int* blocks_per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ip_solve_kernel<D, IP_THREADS>,
-                                                       IP_THREADS, 0);
+  cudaError_t e = prepare_ip<D>();
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ip_solve_kernel<D, IP_THREADS>, IP_THREADS,
+                                                       KernelSmem<D, IP_THREADS>::BYTES);
 }
 
 template <class D>
 cudaError_t launch_ip(const IpParams& p, int sm_count, cudaStream_t s) {
   constexpr int PPW = 32 / D::G;
-  constexpr int PPB = PPW * (IP_THREADS / 32);  // subproblems per CTA pass
+  constexpr int PPB = PPW * (IP_THREADS / 32);  // subproblems in flight per CTA
   int occ = 1;
   cudaError_t e = occupancy_ip<D>(&occ);
   if (e != cudaSuccess) return e;
-  if (occ < 1) occ = 1;
-  int64_t need = (p.n + PPB - 1) / PPB;
-  int64_t cap = (int64_t)sm_count * occ;  // persistent: one wave of resident CTAs
+  if (occ < 1) return cudaErrorLaunchOutOfResources;
+  // persistent grid: one wave of resident CTAs, each owning a contiguous slice of the batch
+  // (a slice of >= 4 passes keeps the knot constants staged in shared memory amortised)
+  int64_t need = (p.n + 4 * PPB - 1) / (4 * PPB);
+  int64_t cap = (int64_t)sm_count * occ;
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
-  ip_solve_kernel<D, IP_THREADS><<<grid, IP_THREADS, 0, s>>>(p);
+  ip_solve_kernel<D, IP_THREADS><<<grid, IP_THREADS, KernelSmem<D, IP_THREADS>::BYTES, s>>>(p);
   return cudaGetLastError();
 }
 
