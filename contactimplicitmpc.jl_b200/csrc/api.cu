@@ -402,7 +402,7 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
   if (rc != CIMPC_OK) return rc;
   if (n == 0) return CIMPC_OK;
   for (int64_t i = 0; i < n; ++i)
-    if (knot[i] < 0 || knot[i] >= ctx->h_ref) return CIMPC_ERR_INVALID_ARGUMENT;
+    if (knot[i] < -1 || knot[i] >= ctx->h_ref) return CIMPC_ERR_INVALID_ARGUMENT;  // −1 = skip
   CK(cudaSetDevice(ctx->device));
   const LinLayout& l = ctx->entry->lay;
   const int nc = ctx->entry->desc.nc;

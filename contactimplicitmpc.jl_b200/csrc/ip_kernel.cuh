@@ -184,35 +184,42 @@ __device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l
   constexpr int NY = D::NY, G = D::G;
   using S = GroupScratch<D>;
   c.mystep = UNPIV;
-  int* pl = reinterpret_cast<int*>(sc + S::O_PL);
+  int* pl = reinterpret_cast<int*>(sc + S::O_PROW + NY);  // O_PL when recorded (see GroupScratch)
+  (void)pl;
 #pragma unroll 1
   for (int kb = 0; kb < NY; kb += 4) {
     static_for<0, 4>([&](auto U) {
       constexpr int u = decltype(U)::value;
+      // partial pivoting on the leading 32 bits of |a| (monotone for non-negative doubles): the chosen
+      // pivot is within 2^-20 of the column maximum, which is all that stability needs
       const bool unp = (c.mystep == UNPIV) && hy;
-      const double cand = unp ? fabs(c.M[u]) : -1.0;
-      const double m = gmax<G>(cand);
+      const unsigned cand = unp ? ((unsigned)__double2hiint(c.M[u]) & 0x7fffffffu) + 1u : 0u;
+      unsigned m = cand;
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o, G));
       unsigned bal = __ballot_sync(FULL, cand == m);
       bal = (G == 32) ? bal : ((bal >> gshift) & ((1u << (G & 31)) - 1u));
       const int p = __ffs(bal) - 1;
       const bool is_p = (l == p);
-      if (is_p) {
+      if (is_p) {  // publish the pivot row, then clear it: every lane's update below is one FMA per column
         c.mystep = kb + u;
-        if (RECORD_PL) pl[kb + u] = l;
+        if (RECORD_PL) reinterpret_cast<int*>(sc + S::O_PL)[kb + u] = l;
         static_for<0, NY / 2>([&](auto J) {
           constexpr int j = decltype(J)::value;
           *reinterpret_cast<double2*>(sc + S::O_PROW + 2 * j) = make_double2(c.M[2 * j], c.M[2 * j + 1]);
+          c.M[2 * j] = 0.0;
+          c.M[2 * j + 1] = 0.0;
         });
       }
       __syncwarp();
       const double pinv = __drcp_rn(sc[S::O_PROW + u]);
-      const double f = c.M[u];
-      const double g = is_p ? pinv : -f * pinv;  // new entry of the pivot column, and update factor
+      // new pivot-column entry = update factor:  pivot row: 1/piv ; other rows: −a_iu / piv
+      const double g = is_p ? pinv : -c.M[u] * pinv;
       static_for<0, NY / 2>([&](auto J) {
         constexpr int j = decltype(J)::value;
         const double2 pr = lds2(sc + S::O_PROW + 2 * j);
-        if constexpr (2 * j != u) c.M[2 * j] = is_p ? pr.x * pinv : fma(g, pr.x, c.M[2 * j]);
-        if constexpr (2 * j + 1 != u) c.M[2 * j + 1] = is_p ? pr.y * pinv : fma(g, pr.y, c.M[2 * j + 1]);
+        if constexpr (2 * j != u) c.M[2 * j] = fma(g, pr.x, c.M[2 * j]);
+        if constexpr (2 * j + 1 != u) c.M[2 * j + 1] = fma(g, pr.y, c.M[2 * j + 1]);
       });
       c.M[u] = g;
       __syncwarp();
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
   double* Ls = reinterpret_cast<double*>(smem_raw);                      // staged knot constants
   double* scratch = Ls + D::SMEM_DOUBLES;                                // per-group scratch
   uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + KS::GROUPS * KS::GS);
-  int* ctl = reinterpret_cast<int*>(bar + 1);  // [0] next subproblem of the segment, [1] segment end, [2] knot
+  int* ctl = reinterpret_cast<int*>(bar + 1);  // [0] next subproblem of the segment, [1] segment end, [3] first active
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int l = lane % G, gi = lane / G, gshift = gi * G;
@@ -385,23 +392,34 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
   uint32_t phase = 0;
 
   for (int64_t cur = c0; cur < c1;) {
-    // ---- segment = maximal run of subproblems on the same reference knot ----
+    // ---- segment = maximal run of subproblems on the same reference knot; knot −1 marks an inactive
+    //      subproblem (finished rollout): it belongs to any segment and is skipped, outputs untouched ----
     if (tid == 0) {
-      const int kn0 = p.knot[cur];
-      ctl[2] = (kn0 < 0 || kn0 >= p.h_ref) ? 0 : kn0;  // range is validated by the host entry point
-      ctl[1] = (int)(c1 - c0);
+      ctl[3] = (int)(c1 - c0);  // first active subproblem at or after cur
+      ctl[1] = (int)(c1 - c0);  // segment end
       ctl[0] = 0;
     }
     __syncthreads();
-    const int kn = ctl[2];
-    const int kraw = p.knot[cur];
-    for (int64_t i = cur + 1 + tid; i < c1; i += THREADS)
-      if (p.knot[i] != kraw) {
-        atomicMin(&ctl[1], (int)(i - c0));
+    for (int64_t i = cur + tid; i < c1; i += THREADS)
+      if (p.knot[i] >= 0) {
+        atomicMin(&ctl[3], (int)(i - c0));
         break;
       }
     __syncthreads();
+    const int64_t first = c0 + ctl[3];
+    if (first >= c1) break;  // nothing left to do in this CTA's slice (CTA-uniform)
+    const int kraw = p.knot[first];
+    const int kn = (kraw >= p.h_ref) ? 0 : kraw;  // range is validated by the host entry point
+    for (int64_t i = first + 1 + tid; i < c1; i += THREADS) {
+      const int ki = p.knot[i];
+      if (ki >= 0 && ki != kraw) {
+        atomicMin(&ctl[1], (int)(i - c0));
+        break;
+      }
+    }
+    __syncthreads();
     const int64_t seg_end = c0 + ctl[1];
+    cur = first;
     if (kn != staged) {  // CTA-uniform
       if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)(D::SMEM_DOUBLES * 8));
@@ -422,8 +440,9 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
       const int64_t wb = cur + base;
       if (wb >= seg_end) break;
       const int64_t prob = wb + gi;
-      const bool valid = prob < seg_end;
-      const int64_t pi = valid ? prob : wb;  // idle groups shadow the warp's first subproblem
+      const bool valid = prob < seg_end && p.knot[prob] >= 0;
+      if (!__any_sync(FULL, valid)) continue;
+      const int64_t pi = valid ? prob : (int64_t)first;  // idle groups shadow an active subproblem
 
       Ctx<D> c;
       // prologue: θ-dependent constants  c = c0 + Rθ θ (+ alt on the impact rows)
@@ -488,9 +507,11 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
         __syncwarp();
 
         // ---- predictor (affine) direction: only Δy1, Δy2 are needed ----
-        double t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * c.rbil / y1r) : 0.0);
+        // (the five divisions by ŷ1 of one iteration share one correctly-rounded reciprocal)
+        const double iy1 = __drcp_rn(y1r);
+        double t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * c.rbil * iy1) : 0.0);
         const double dy1a = -t;
-        const double dy2a = hy ? (c.rbil - y2r * dy1a) / y1r : 0.0;
+        const double dy2a = hy ? (c.rbil - y2r * dy1a) * iy1 : 0.0;
         const double a_aff = step_length<D>(hy, c.y1, c.y2, dy1a, dy2a, 1.0);
         const double mu = gsum<G>(hy ? c.y1 * c.y2 : 0.0) / (double)NY;
         const double mu_aff = gsum<G>(hy ? (c.y1 - a_aff * dy1a) * (c.y2 - a_aff * dy2a) : 0.0) / (double)NY;
@@ -500,9 +521,9 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
 
         // ---- corrector: rbil = y1∘y2 − κ + Δy1aff∘Δy2aff ----
         const double rbc = hy ? fma(c.y1, c.y2, -kap) + dy1a * dy2a : 0.0;
-        t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * rbc / y1r) : 0.0);
+        t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * rbc * iy1) : 0.0);
         const double dy1 = -t;
-        const double dy2 = hy ? (rbc - y2r * dy1) / y1r : 0.0;
+        const double dy2 = hy ? (rbc - y2r * dy1) * iy1 : 0.0;
         double dx = au;
         {
           const double* AB = Ls + D::O_AIBC + l;

@@ -119,7 +119,8 @@ int cimpc_upload_linearization(cimpc_ctx* ctx, int32_t H_ref, const double* z0, 
  *     for t in window[1:end-2]: z_initialize!; ip[t].θ .= traj.θ[i]; interior_point_solve!(ip[t])
  * of `implicit_dynamics!` (src/controller/implicit_dynamics.jl:156-192) for `n` independent
  * (rollout × stage × Newton-evaluation) subproblems.  DEVICE pointers:
- *   knot    n            int32, 0-based reference knot of each problem (`t − 1` of `window`)
+ *   knot    n            int32, 0-based reference knot of each problem (`t − 1` of `window`);
+ *                        −1 marks an inactive subproblem: it is skipped and its outputs are left untouched
  *   theta   nθ × n       problem data θ                     (`traj.θ[i]`)
  *   q2_init nq × n       cold-start configuration; z = 1, z[q2] = q2_init  (`z_initialize!`,
  *                        src/simulation/simulation.jl:59-63)
