@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rollouts", type=int, default=ROLLOUTS_PER_GPU, help="rollouts per GPU (default 65536)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mpc", action="store_true", help="skip the batched newton_solve! (MPC steps/s) leg")
+    ap.add_argument("--mpc-rollouts", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -301,6 +303,43 @@ def main():
     e2e_s = float(te.item())
     e2e_ok = bool(np.array_equal(z_h.numpy(), outb[0].cpu().numpy()))
 
+    # ---- MPC-step leg: batched newton_solve! (cold start, one MPC step of every rollout) --------------
+    mpc = None
+    if not args.no_mpc:
+        from common import load_gait
+        gait = load_gait(ROBOT)
+        Rm = min(args.rollouts, args.mpc_rollouts)
+        oq = np.tile(1e-2 * np.array([1.0, 0.02, 0.25] + [0.75] * (nq - 3)), (H_MPC, 1))  # monte_carlo.jl:33-37
+        ou = np.tile(3e-2 * np.ones(nu), (H_MPC, 1))
+        newton = cb.Newton(im, H_MPC, Rm, oq, ou, 1.0e-4, cb.NewtonOptions(r_tol=3e-4, max_iter=5), ip_opts=opts)
+        rng = np.random.Generator(np.random.Philox(1000 + rank))
+        q0m = torch.from_numpy(np.tile(gait["q"][0], (Rm, 1))).to(dev)
+        q1m = torch.from_numpy(gait["q"][1] + 0.01 * rng.standard_normal((Rm, nq))).to(dev)
+        win = np.arange(H_MPC + 2, dtype=np.int32)
+        newton.solve(win, gait["q"][:H_MPC + 2], gait["u"][:H_MPC], gait["mu"], gait["h"], q0m, q1m)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        m_steps = 3
+        l0 = im.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(m_steps):
+            um, _, infom = newton.solve(win, gait["q"][:H_MPC + 2], gait["u"][:H_MPC], gait["mu"], gait["h"], q0m, q1m)
+        e1.record()
+        torch.cuda.synchronize()
+        tm = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        inf = infom.double().mean(0).cpu().numpy()
+        mpc = {"value": Rm * world * m_steps / (float(tm.item()) * 1e-3), "unit": "MPC steps/s",
+               "rollouts_per_gpu": Rm, "steps": m_steps, "ms_per_mpc_step_batch": float(tm.item()) / m_steps,
+               "mean_newton_iterations": float(inf[0]), "mean_implicit_dynamics_sweeps": float(inf[1]),
+               "converged_frac": float(inf[2]), "sweeps_per_call": newton.last_sweeps,
+               "gpu_launches": int(im.launch_count - l0),
+               "config": "newton_solve! cold start, quadruped H_mpc=10, r_tol=3e-4, max_iter=5 (monte_carlo.jl:44-48), "
+                         "q1 = reference + N(0, 0.01^2)"}
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -343,6 +382,8 @@ def main():
                  "flops_per_subproblem": fl, "peak_source": f_kind,
                  "note": "flops counted as the REFERENCE algorithm would spend them (BASELINE.md §3)"},
     }
+    if mpc is not None:
+        out["mpc_steps"] = mpc
     if not args.no_cpu_baseline and world == 1:
         sample = min(n, 262144)
         v, cores, dt, mit, conv = cpu_baseline_run(lin, knot, theta, q2, sample)

@@ -2,4 +2,6 @@
 dojo-sim/ContactImplicitMPC.jl).  The directory name carries a dot, so import it through the
 repo-root shim:  `import cimpc_b200`."""
 from .capi import LIB_PATH, SYMBOLS, CimpcError, load_library  # noqa: F401
-from .solver import ImplicitTrajectory, InteriorPointOptions, implicit_dynamics  # noqa: F401
+from .solver import (ImplicitTrajectory, InteriorPointOptions, Newton, NewtonOptions,  # noqa: F401
+                     implicit_dynamics)
+from .sharding import gather_rollout_results, shard_rollouts, sum_statistics  # noqa: F401,E402

@@ -18,6 +18,7 @@ SYMBOLS = [
     "cimpc_ip_opts_default", "cimpc_status_string", "cimpc_last_cuda_error", "cimpc_version",
     "cimpc_create", "cimpc_destroy", "cimpc_get_dims", "cimpc_upload_linearization",
     "cimpc_ip_solve_batch", "cimpc_ip_solve_batch_host", "cimpc_launch_count",
+    "cimpc_newton_opts_default", "cimpc_newton_create", "cimpc_newton_solve_batch", "cimpc_newton_last_sweeps",
 ]
 
 
@@ -36,6 +37,10 @@ class IPOpts(C.Structure):
                 ("kappa_reg", C.c_double), ("gamma_reg", C.c_double), ("undercut", C.c_double),
                 ("ls_scale", C.c_double), ("max_iter", C.c_int32), ("max_ls", C.c_int32),
                 ("diff_sol", C.c_int32), ("reserved", C.c_int32)]
+
+
+class NewtonOpts(C.Structure):
+    _fields_ = [("r_tol", C.c_double), ("beta_init", C.c_double), ("max_iter", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CimpcError(RuntimeError):
@@ -80,6 +85,14 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_ip_solve_batch_host.restype = C.c_int
     lib.cimpc_launch_count.argtypes = [vp]
     lib.cimpc_launch_count.restype = C.c_int64
+    lib.cimpc_newton_opts_default.argtypes = [C.POINTER(NewtonOpts)]
+    lib.cimpc_newton_opts_default.restype = None
+    lib.cimpc_newton_create.argtypes = [vp, i32, i64, dp, dp, C.c_double, C.POINTER(NewtonOpts), C.POINTER(IPOpts)]
+    lib.cimpc_newton_create.restype = C.c_int
+    lib.cimpc_newton_solve_batch.argtypes = [vp, dp, dp, dp, C.c_double, C.c_double, dp, dp, i32, dp, dp, dp, vp]
+    lib.cimpc_newton_solve_batch.restype = C.c_int
+    lib.cimpc_newton_last_sweeps.argtypes = [vp]
+    lib.cimpc_newton_last_sweeps.restype = i32
     _lib = lib
     return lib
 

@@ -209,6 +209,21 @@ struct cimpc_ctx {
   static constexpr int NS = 3;            // pipeline depth of the host entry point
   static constexpr int64_t CHUNK = 32768;  // subproblems per pipelined chunk
   cudaStream_t streams[NS] = {nullptr, nullptr, nullptr};
+  // device Newton state (cimpc_newton_create)
+  struct NewtonState {
+    NewtonParams p{};
+    void* arena = nullptr;
+    cimpc_ip_opts ip{};
+    cimpc_newton_opts no{};
+    double *z = nullptr, *dz = nullptr, *ref_q = nullptr, *ref_u = nullptr, *w = nullptr, *obj_q = nullptr,
+           *obj_u = nullptr;
+    int32_t* window = nullptr;
+    uint8_t* status = nullptr;
+    int32_t* iters = nullptr;
+    int* h_active = nullptr;  // pinned
+    int32_t last_sweeps = 0;
+    bool ready = false;
+  } nw;
 };
 
 static int cuda_fail(cimpc_ctx* c, cudaError_t e, const char* where) {
@@ -233,6 +248,22 @@ static const ModelEntry* find_entry(const cimpc_model_desc& d) {
 #undef CIMPC_SEARCH
   return nullptr;
 }
+
+__global__ void newton_finish_kernel(const NewtonParams p, int nq, int nu, double* u_out, double* q_out, int32_t* info,
+                                     double r_tol, int len) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.R) return;
+  for (int k = 0; k < nu; ++k) u_out[(size_t)r * nu + k] = p.traj_u[(size_t)r * p.H * nu + k];
+  if (q_out)
+    for (int e = 0; e < (p.H + 2) * nq; ++e) q_out[(size_t)r * (p.H + 2) * nq + e] = p.traj_q[(size_t)r * (p.H + 2) * nq + e];
+  if (info) {
+    info[4 * r + 0] = p.newton_it[r];
+    info[4 * r + 1] = p.sweeps[r];
+    info[4 * r + 2] = (p.r_norm[r] / (double)len < r_tol) ? 1 : 0;
+    info[4 * r + 3] = p.phase[r];
+  }
+}
+
 
 extern "C" {
 
@@ -295,6 +326,8 @@ int cimpc_destroy(cimpc_ctx* ctx) {
   if (!ctx) return CIMPC_OK;
   cudaSetDevice(ctx->device);
   if (ctx->lin) cudaFree(ctx->lin);
+  if (ctx->nw.arena) cudaFree(ctx->nw.arena);
+  if (ctx->nw.h_active) cudaFreeHost(ctx->nw.h_active);
   if (ctx->dev) cudaFree(ctx->dev);
   if (ctx->pin) cudaFreeHost(ctx->pin);
   for (int i = 0; i < cimpc_ctx::NS; ++i)
@@ -480,6 +513,119 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
     CK(cudaStreamSynchronize(ctx->streams[c % NS]));
     if (!pin_out) drain(c);
   }
+  return CIMPC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Device Newton
+// ------------------------------------------------------------------------------------------
+void cimpc_newton_opts_default(cimpc_newton_opts* o) {
+  if (!o) return;
+  o->r_tol = 1e-5; o->beta_init = 1e-5; o->max_iter = 10; o->reserved = 0;
+}
+
+int32_t cimpc_newton_last_sweeps(const cimpc_ctx* ctx) { return ctx ? ctx->nw.last_sweeps : 0; }
+
+int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q, const double* obj_u,
+                        double kappa, const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts) {
+  if (!ctx || H < 1 || H > 64 || R64 < 1 || R64 > (1 << 30) / H || !obj_q || !obj_u || !nopts || !ip_opts)
+    return CIMPC_ERR_INVALID_ARGUMENT;
+  if (!ctx->entry->newton_step) return CIMPC_ERR_UNSUPPORTED_MODEL;  // :configurationforce instance
+  if (!ctx->lin) return CIMPC_ERR_NOT_INITIALIZED;
+  CK(cudaSetDevice(ctx->device));
+  auto& nw = ctx->nw;
+  if (nw.arena) { cudaFree(nw.arena); nw.arena = nullptr; }
+  nw.ready = false;
+  const LinLayout& l = ctx->entry->lay;
+  const cimpc_model_desc& d = ctx->entry->desc;
+  const int R = (int)R64, nq = d.nq, nu = d.nu, nw_ = d.nw, nd = l.nd, nth = l.nth, nz = l.nz, ncol = l.ncol;
+  const size_t n = (size_t)H * R;
+  // carve one arena
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_tq = take(sizeof(double) * R * (H + 2) * nq), o_tu = take(sizeof(double) * R * H * nu),
+               o_nu = take(sizeof(double) * R * H * nd), o_cq = take(sizeof(double) * R * (H + 2) * nq),
+               o_cu = take(sizeof(double) * R * H * nu), o_cnu = take(sizeof(double) * R * H * nd),
+               o_dl = take(sizeof(double) * R * H * (nu + nq + nd)), o_rn = take(sizeof(double) * R),
+               o_al = take(sizeof(double) * R), o_be = take(sizeof(double) * R), o_ls = take(sizeof(int) * R),
+               o_ni = take(sizeof(int) * R), o_sw = take(sizeof(int) * R), o_ph = take(sizeof(int) * R),
+               o_kn = take(sizeof(int32_t) * n), o_th = take(sizeof(double) * n * nth), o_q2 = take(sizeof(double) * n * nq),
+               o_z = take(sizeof(double) * n * nz), o_dz = take(sizeof(double) * n * nd * ncol), o_st = take(n),
+               o_it = take(sizeof(int32_t) * n), o_na = take(sizeof(int)), o_rq = take(sizeof(double) * (H + 2) * nq),
+               o_ru = take(sizeof(double) * H * nu), o_w = take(sizeof(double) * H * (nw_ > 0 ? nw_ : 1)),
+               o_win = take(sizeof(int32_t) * (H + 2)), o_oq = take(sizeof(double) * H * nq),
+               o_ou = take(sizeof(double) * H * nu);
+  CK(cudaMalloc(&nw.arena, off));
+  CK(cudaMemset(nw.arena, 0, off));
+  char* b = (char*)nw.arena;
+  NewtonParams& p = nw.p;
+  p.R = R; p.H = H;
+  p.traj_q = (double*)(b + o_tq); p.traj_u = (double*)(b + o_tu); p.nu = (double*)(b + o_nu);
+  p.cand_q = (double*)(b + o_cq); p.cand_u = (double*)(b + o_cu); p.cand_nu = (double*)(b + o_cnu);
+  p.delta = (double*)(b + o_dl); p.r_norm = (double*)(b + o_rn); p.alpha = (double*)(b + o_al);
+  p.beta = (double*)(b + o_be); p.ls_it = (int*)(b + o_ls); p.newton_it = (int*)(b + o_ni);
+  p.sweeps = (int*)(b + o_sw); p.phase = (int*)(b + o_ph); p.knot = (int32_t*)(b + o_kn);
+  p.theta = (double*)(b + o_th); p.q2 = (double*)(b + o_q2);
+  nw.z = (double*)(b + o_z); nw.dz = (double*)(b + o_dz); nw.status = (uint8_t*)(b + o_st); nw.iters = (int32_t*)(b + o_it);
+  p.z = nw.z; p.dz = nw.dz; p.n_active = (int*)(b + o_na);
+  nw.ref_q = (double*)(b + o_rq); nw.ref_u = (double*)(b + o_ru); nw.w = (double*)(b + o_w);
+  nw.window = (int32_t*)(b + o_win); nw.obj_q = (double*)(b + o_oq); nw.obj_u = (double*)(b + o_ou);
+  p.ref_q = nw.ref_q; p.ref_u = nw.ref_u; p.w = nw.w; p.window = nw.window; p.obj_q = nw.obj_q; p.obj_u = nw.obj_u;
+  p.kappa = kappa; p.r_tol = nopts->r_tol; p.beta_init = nopts->beta_init; p.max_iter = nopts->max_iter;
+  CK(cudaMemcpy(nw.obj_q, obj_q, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(nw.obj_u, obj_u, sizeof(double) * H * nu, cudaMemcpyHostToDevice));
+  if (!nw.h_active) CK(cudaMallocHost(&nw.h_active, sizeof(int)));
+  nw.ip = *ip_opts;
+  nw.ip.diff_sol = 1;
+  nw.no = *nopts;
+  nw.ready = true;
+  return CIMPC_OK;
+}
+
+int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
+                             double mu, double h, const double* q0, const double* q1, int32_t warm_start,
+                             double* u_out, double* q_out, int32_t* info, void* stream) {
+  if (!ctx || !window || !ref_q || !ref_u || !q0 || !q1 || !u_out) return CIMPC_ERR_INVALID_ARGUMENT;
+  auto& nw = ctx->nw;
+  if (!nw.ready) return CIMPC_ERR_NOT_INITIALIZED;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  NewtonParams& p = nw.p;
+  const cimpc_model_desc& d = ctx->entry->desc;
+  const int H = p.H, R = p.R;
+  for (int t = 0; t < H; ++t)
+    if (window[t] < 0 || window[t] >= ctx->h_ref) return CIMPC_ERR_INVALID_ARGUMENT;
+  p.mu = mu; p.h = h;
+  CK(cudaMemcpyAsync(nw.window, window, sizeof(int32_t) * (H + 2), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(nw.ref_q, ref_q, sizeof(double) * (H + 2) * d.nq, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(nw.ref_u, ref_u, sizeof(double) * H * d.nu, cudaMemcpyHostToDevice, s));
+  *nw.h_active = R;
+  CK(cudaMemcpyAsync(p.n_active, nw.h_active, sizeof(int), cudaMemcpyHostToDevice, s));
+  cudaError_t e = ctx->entry->newton_reset(p, q0, q1, warm_start ? 1 : 0, s);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_reset_kernel launch");
+  ctx->launches++;
+  // worst case: 1 + max_iter·(1 + 7) sweeps (newton.jl:202-269); stop as soon as no rollout is active
+  const int max_rounds = 1 + p.max_iter * 8 + 1;
+  int sweeps = 0;
+  for (int round = 0; round < max_rounds; ++round) {
+    int rc = cimpc_ip_solve_batch(ctx, (int64_t)H * R, p.knot, p.theta, p.q2, nullptr, &nw.ip, nw.z, nw.dz, nw.status,
+                                  nw.iters, s);
+    if (rc != CIMPC_OK) return rc;
+    ++sweeps;
+    e = ctx->entry->newton_step(p, s);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_step_kernel launch");
+    ctx->launches++;
+    CK(cudaMemcpyAsync(nw.h_active, p.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (*nw.h_active <= 0) break;
+  }
+  nw.last_sweeps = sweeps;
+  const int len = H * (d.nu + d.nq + ctx->entry->lay.nd);
+  newton_finish_kernel<<<(R + 127) / 128, 128, 0, s>>>(p, d.nq, d.nu, u_out, q_out, info, p.r_tol, len);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_finish_kernel launch");
+  ctx->launches++;
   return CIMPC_OK;
 }
 

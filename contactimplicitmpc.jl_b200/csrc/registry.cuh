@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "ip_kernel.cuh"
+#include "newton_kernel.cuh"
 
 namespace cimpc {
 
@@ -18,7 +19,32 @@ struct ModelEntry {
   LinLayout lay;
   cudaError_t (*launch)(const IpParams& p, int sm_count, cudaStream_t s);
   cudaError_t (*occupancy)(int* blocks_per_sm);
+  // device Newton (:configuration instances only, else null)
+  cudaError_t (*newton_reset)(const NewtonParams& p, const double* q0, const double* q1, int warm, cudaStream_t s);
+  cudaError_t (*newton_step)(const NewtonParams& p, cudaStream_t s);
 };
+
+constexpr int NEWTON_THREADS = 128;
+
+template <class D>
+cudaError_t launch_newton_reset(const NewtonParams& p, const double* q0, const double* q1, int warm, cudaStream_t s) {
+  newton_reset_kernel<D, NEWTON_THREADS><<<p.R, NEWTON_THREADS, 0, s>>>(p, q0, q1, warm);
+  return cudaGetLastError();
+}
+
+template <class D>
+cudaError_t launch_newton_step(const NewtonParams& p, cudaStream_t s) {
+  const size_t bytes = (size_t)NewtonSmem<D>::doubles(p.H) * sizeof(double);
+  static size_t configured = 0;
+  if (bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(newton_step_kernel<D, NEWTON_THREADS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured = bytes;
+  }
+  newton_step_kernel<D, NEWTON_THREADS><<<p.R, NEWTON_THREADS, bytes, s>>>(p);
+  return cudaGetLastError();
+}
 
 constexpr int IP_THREADS = 256;
 
@@ -76,8 +102,10 @@ CIMPC_FOR_EACH_MODEL(CIMPC_DECLARE_ENTRY)
     using D0 = Dims<nq, nu, nw, nc, nb, 0>;                                                       \
     using D1 = Dims<nq, nu, nw, nc, nb, 1>;                                                       \
     static const ModelEntry e[2] = {                                                              \
-        {#name_, {nq, nu, nw, nc, nb, 0}, layout_of<D0>(), &launch_ip<D0>, &occupancy_ip<D0>},    \
-        {#name_, {nq, nu, nw, nc, nb, 1}, layout_of<D1>(), &launch_ip<D1>, &occupancy_ip<D1>}};   \
+        {#name_, {nq, nu, nw, nc, nb, 0}, layout_of<D0>(), &launch_ip<D0>, &occupancy_ip<D0>,     \
+         &launch_newton_reset<D0>, &launch_newton_step<D0>},                                      \
+        {#name_, {nq, nu, nw, nc, nb, 1}, layout_of<D1>(), &launch_ip<D1>, &occupancy_ip<D1>,     \
+         nullptr, nullptr}};                                                                      \
     *count = 2;                                                                                   \
     return e;                                                                                     \
   }

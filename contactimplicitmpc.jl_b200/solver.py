@@ -38,6 +38,17 @@ class InteriorPointOptions:
                            self.undercut, self.ls_scale, self.max_iter, self.max_ls, int(self.diff_sol), 0)
 
 
+@dataclass
+class NewtonOptions:
+    """`NewtonOptions` (src/controller/newton.jl:2-11); `max_time` is replaced by the iteration caps."""
+    r_tol: float = 1.0e-5
+    max_iter: int = 10
+    beta_init: float = 1.0e-5
+
+    def to_c(self) -> capi.NewtonOpts:
+        return capi.NewtonOpts(self.r_tol, self.beta_init, self.max_iter, 0)
+
+
 MODES = {"configuration": 0, "configurationforce": 1}
 
 
@@ -179,6 +190,56 @@ class ImplicitTrajectory:
             dz.data_ptr() if dz is not None else None, status.data_ptr(), iters.data_ptr(),
             C.c_void_p(stream)))
         return z, dz, status, iters
+
+
+class Newton:
+    """Batched `Newton` core (src/controller/newton.jl:17-91) for `n_rollouts` rollouts sharing one
+    reference window; `solve` is `newton_solve!` (newton.jl:169-288) for all of them — one MPC step.
+
+    obj_q (H, nq), obj_u (H, nu): diagonals of the `TrackingObjective` weights (objective.jl:3-16).
+    All heavy work (implicit-dynamics sweeps + KKT solves + line searches) runs on the GPU."""
+
+    def __init__(self, im_traj: ImplicitTrajectory, H_mpc: int, n_rollouts: int, obj_q, obj_u, kappa: float,
+                 opts: NewtonOptions | None = None, ip_opts: InteriorPointOptions | None = None):
+        if im_traj.mode != "configuration":
+            raise ValueError("device Newton supports mode='configuration'")
+        self.im = im_traj
+        self.H, self.R = int(H_mpc), int(n_rollouts)
+        self.opts = opts or NewtonOptions()
+        self.ip_opts = ip_opts or im_traj.opts
+        oq = _f64(obj_q, (self.H, im_traj.nq))
+        ou = _f64(obj_u, (self.H, im_traj.nu))
+        co, ci = self.opts.to_c(), self.ip_opts.to_c()
+        capi.check(im_traj._ctx, im_traj.lib.cimpc_newton_create(
+            im_traj._ctx, self.H, self.R, oq.ctypes.data, ou.ctypes.data, float(kappa), C.byref(co), C.byref(ci)))
+
+    def solve(self, window, ref_q, ref_u, mu, h, q0, q1, warm_start=False, want_q=False, stream=None):
+        """window: (H+2,) 0-based knots; ref_q (H+2, nq), ref_u (H, nu) host arrays (shared by all rollouts);
+        q0, q1: torch CUDA (R, nq) fp64.  Returns u (R, nu), q (R, H+2, nq) or None, info (R, 4) int32
+        [Newton iterations, sweeps, converged, phase] as torch CUDA tensors."""
+        import torch
+        im = self.im
+        window = np.ascontiguousarray(window, dtype=np.int32)
+        assert window.shape == (self.H + 2,)
+        ref_q = _f64(ref_q, (self.H + 2, im.nq))
+        ref_u = _f64(ref_u, (self.H, im.nu))
+        for t_ in (q0, q1):
+            assert t_.is_cuda and t_.dtype == torch.float64 and t_.is_contiguous() and t_.shape == (self.R, im.nq)
+        dev = q0.device
+        u = torch.empty((self.R, im.nu), dtype=torch.float64, device=dev)
+        q = torch.empty((self.R, self.H + 2, im.nq), dtype=torch.float64, device=dev) if want_q else None
+        info = torch.empty((self.R, 4), dtype=torch.int32, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        capi.check(im._ctx, im.lib.cimpc_newton_solve_batch(
+            im._ctx, window.ctypes.data, ref_q.ctypes.data, ref_u.ctypes.data, float(mu), float(h), q0.data_ptr(),
+            q1.data_ptr(), int(bool(warm_start)), u.data_ptr(), q.data_ptr() if q is not None else None,
+            info.data_ptr(), C.c_void_p(stream)))
+        return u, q, info
+
+    @property
+    def last_sweeps(self) -> int:
+        return int(self.im.lib.cimpc_newton_last_sweeps(self.im._ctx))
 
 
 def implicit_dynamics(im_traj: ImplicitTrajectory, knot, theta, q2, gamma=None, b=None, alt=None,

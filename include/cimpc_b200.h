@@ -148,6 +148,57 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
                               const double* q2_init, const double* alt, const cimpc_ip_opts* opts,
                               double* z_out, double* dz_out, uint8_t* status, int32_t* iters);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched `newton_solve!` (src/controller/newton.jl:169-288) for n_rollouts Monte-Carlo rollouts that
+ * track the same reference window (policy.jl:100-107, 131): one call = one MPC step of every rollout.
+ * :configuration mode with a `TrackingObjective` (diagonal weights), the configuration of the
+ * reference's Monte-Carlo examples (examples/quadruped/monte_carlo.jl:33-58).
+ * ------------------------------------------------------------------------------------------------ */
+
+/* `NewtonOptions` (src/controller/newton.jl:2-11); `max_time` is replaced by the iteration caps. */
+typedef struct cimpc_newton_opts {
+  double r_tol;     /* r_norm / length(r) tolerance          default 1e-5 (MPC examples: 3e-4) */
+  double beta_init; /* initial dual regularisation β_init    default 1e-5                      */
+  int32_t max_iter; /* Newton iterations                     default 10  (MPC examples: 5)     */
+  int32_t reserved;
+} cimpc_newton_opts;
+
+void cimpc_newton_opts_default(cimpc_newton_opts* opts);
+
+/*
+ * Allocate the per-rollout Newton state (`Newton(s, H_mpc, h, traj, im_traj; obj, opts)`,
+ * src/controller/newton.jl:37-91).  HOST pointers, Julia column-major:
+ *   obj_q  nq × H_mpc   diagonals of `obj.q[t]`        obj_u  nu × H_mpc   diagonals of `obj.u[t]`
+ * (`TrackingObjective`, src/controller/objective.jl:3-16; γ/b weights are unused in :configuration mode).
+ * kappa = `im_traj.ip[1].κ[1]` (the dual regularisation is H·β·κ, newton_jacobian.jl:185).
+ * Requires a context created with mode = 0 and an uploaded linearization.  Calling it again
+ * re-allocates (e.g. for another batch size).
+ */
+int cimpc_newton_create(cimpc_ctx* ctx, int32_t H_mpc, int64_t n_rollouts, const double* obj_q,
+                        const double* obj_u, double kappa, const cimpc_newton_opts* nopts,
+                        const cimpc_ip_opts* ip_opts);
+
+/*
+ * `newton_solve!(core, s, q0, q1, window, im_traj, ref_traj; warm_start)` for every rollout.
+ *   window   H_mpc + 2    HOST int32, 0-based knots (`p.window .- 1`)
+ *   ref_q    nq × (H_mpc+2), ref_u  nu × H_mpc     HOST: `ref_traj.q[1:H+2]`, `ref_traj.u[1:H]` (the rotated,
+ *            strided copy `p.traj` the policy passes, policy.jl:119-120);  mu, h: `θ` entries μ and h
+ *   q0, q1   nq × n_rollouts   DEVICE: `p.q0` and the measured `traj.q[t+1]` of every rollout
+ *   warm_start  0: duals ← 0 and trajectory ← reference (newton.jl:139-151); 1: keep the previous solution
+ * Outputs (DEVICE):
+ *   u_out    nu × n_rollouts       `core.traj.u[1]`  (the policy returns it divided by N_sample, policy.jl:141-144)
+ *   q_out    nq × (H_mpc+2) × n_rollouts   optimised configurations `core.traj.q`, or NULL
+ *   info     4 × n_rollouts int32  [Newton iterations, implicit_dynamics! sweeps, converged(0/1), reserved], or NULL
+ * The call runs asynchronously on `stream` except for one 4-byte read per sweep (termination test).
+ */
+int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
+                             double mu, double h, const double* q0, const double* q1, int32_t warm_start,
+                             double* u_out, double* q_out, int32_t* info, void* stream);
+
+/* Sweeps (= ip_solve_kernel launches) used by the last cimpc_newton_solve_batch call. */
+int32_t cimpc_newton_last_sweeps(const cimpc_ctx* ctx);
+
 /* Number of kernel launches issued through this context so far (bench bookkeeping). */
 int64_t cimpc_launch_count(const cimpc_ctx* ctx);
 
