@@ -220,6 +220,7 @@ struct cimpc_ctx {
     int32_t* window = nullptr;
     uint8_t* status = nullptr;
     int32_t* iters = nullptr;
+    double* lscratch = nullptr;  // factor block columns of every rollout
     int* h_active = nullptr;  // pinned
     int32_t last_sweeps = 0;
     bool ready = false;
@@ -555,7 +556,8 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
                o_it = take(sizeof(int32_t) * n), o_na = take(sizeof(int)), o_rq = take(sizeof(double) * (H + 2) * nq),
                o_ru = take(sizeof(double) * H * nu), o_w = take(sizeof(double) * H * (nw_ > 0 ? nw_ : 1)),
                o_win = take(sizeof(int32_t) * (H + 2)), o_oq = take(sizeof(double) * H * nq),
-               o_ou = take(sizeof(double) * H * nu);
+               o_ou = take(sizeof(double) * H * nu),
+               o_lsc = take(sizeof(double) * R * ctx->entry->newton_scratch(H));
   CK(cudaMalloc(&nw.arena, off));
   CK(cudaMemset(nw.arena, 0, off));
   char* b = (char*)nw.arena;
@@ -572,6 +574,7 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
   nw.ref_q = (double*)(b + o_rq); nw.ref_u = (double*)(b + o_ru); nw.w = (double*)(b + o_w);
   nw.window = (int32_t*)(b + o_win); nw.obj_q = (double*)(b + o_oq); nw.obj_u = (double*)(b + o_ou);
   p.ref_q = nw.ref_q; p.ref_u = nw.ref_u; p.w = nw.w; p.window = nw.window; p.obj_q = nw.obj_q; p.obj_u = nw.obj_u;
+  nw.lscratch = (double*)(b + o_lsc);
   p.kappa = kappa; p.r_tol = nopts->r_tol; p.beta_init = nopts->beta_init; p.max_iter = nopts->max_iter;
   CK(cudaMemcpy(nw.obj_q, obj_q, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(nw.obj_u, obj_u, sizeof(double) * H * nu, cudaMemcpyHostToDevice));
@@ -613,7 +616,7 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
                                   nw.iters, s);
     if (rc != CIMPC_OK) return rc;
     ++sweeps;
-    e = ctx->entry->newton_step(p, s);
+    e = ctx->entry->newton_step(p, nw.lscratch, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_step_kernel launch");
     ctx->launches++;
     CK(cudaMemcpyAsync(nw.h_active, p.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -59,140 +59,123 @@ template <class D>
 struct NewtonSmem {
   static constexpr int NQ = D::NQ, NU = D::NU, ND = D::ND, NCOL = D::NCOL;
   static_assert(D::MODE == 0, "device Newton: :configuration mode");
-  static constexpr int KD = 3 * ND - 1;   // half bandwidth of the block-pentadiagonal Schur complement
-  static constexpr int LDB = KD + 1;
-  __host__ __device__ static constexpr int doubles(int H) {
-    return H * ND * NCOL            // dz of the H stages
-           + LDB * H * ND           // banded Y
-           + (H + 2) * NQ + H * NU  // candidate q, u
-           + 3 * H * ND             // ν_cand, g / Δν, d
-           + H * (NU + NQ)          // r_x
-           + 2 * H * (NU + NQ)      // Q⁻¹ (as vectors), v = Q⁻¹ r_x
-           + 64;
+  static_assert(ND <= 32, "one lane per block row");
+  static constexpr int BS = ND * ND;  // one ND×ND block, column-major
+  // per-warp shared memory (doubles): candidate q, u, ν; rhs/solution; d; r_x; six sliding-window blocks
+  __host__ __device__ static constexpr int per_warp(int H) {
+    return (H + 2) * NQ + H * NU + 3 * H * ND + H * (NU + NQ) + 6 * BS + 8;
   }
+  // global scratch per rollout: the three block columns L_tt, L_{t+1,t}, L_{t+2,t} of every stage
+  __host__ __device__ static constexpr size_t l_doubles(int H) { return (size_t)H * 3 * BS; }
 };
 
+constexpr int NEWTON_WARPS = 4;  // rollouts per CTA (one warp each)
+
+// One warp per rollout; everything is warp-synchronous (no __syncthreads).
+//
+// KKT solve.  Y = C Q⁻¹ Cᵀ + ρI is block-pentadiagonal (H×H blocks of nd).  It is assembled, factorised
+// (block Cholesky) and forward-substituted one block column at a time inside a six-block sliding window
+// in shared memory; the factor's block columns go to a global scratch (L2-resident) for the backward pass.
 template <class D, int THREADS>
-__global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams p) {
+__global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams p, double* __restrict__ lscratch) {
   constexpr int NQ = D::NQ, NU = D::NU, NW = D::NW, ND = D::ND, NCOL = D::NCOL, NZ = D::NZ, NTH = D::NTH;
   constexpr int NR = NU + NQ;  // primal block of one stage: [u_t; q_{t+2}]
   using SM = NewtonSmem<D>;
-  constexpr int KD = SM::KD, LDB = SM::LDB;
-  const int r = blockIdx.x, tid = threadIdx.x, H = p.H, R = p.R;
+  constexpr int BS = SM::BS;
+  constexpr unsigned FULLM = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, H = p.H, R = p.R;
+  const int r = blockIdx.x * (THREADS / 32) + wid;
   if (r >= R) return;
-  int phase = p.phase[r];
+  const int phase = p.phase[r];
   if (phase == NP_DONE) return;
-  const int N = H * ND;  // dual dimension
 
   extern __shared__ __align__(16) double sm[];
-  double* DZ = sm;                       // [t][col][row]
-  double* Yb = DZ + H * ND * NCOL;       // banded lower: Yb[(i-j) + j*LDB]
-  double* cq = Yb + LDB * N;             // (H+2)×NQ
-  double* cu = cq + (H + 2) * NQ;        // H×NU
-  double* cnu = cu + H * NU;             // H×ND
-  double* gv = cnu + H * ND;             // H×ND   rhs, then Δν
-  double* dv = gv + H * ND;              // H×ND   d_t
-  double* rx = dv + H * ND;              // H×NR   [r_u; r_q] per stage
-  double* qi = rx + H * NR;              // H×NR   Q⁻¹
-  double* vx = qi + H * NR;              // H×NR   Q⁻¹ r_x
-  double* red = vx + H * NR;             // reduction scratch (64)
-  __shared__ int s_action;               // 0: re-evaluate at a smaller α, 1: solve for a new direction, 2: finished
-  __shared__ double s_alpha;
+  double* base = sm + (size_t)wid * SM::per_warp(H);
+  double* cq = base;                    // (H+2)×NQ
+  double* cu = cq + (H + 2) * NQ;       // H×NU
+  double* cnu = cu + H * NU;            // H×ND
+  double* gv = cnu + H * ND;            // H×ND   rhs → y → Δν
+  double* dv = gv + H * ND;             // H×ND   d_t
+  double* rx = dv + H * ND;             // H×NR   [r_u; r_q] per stage
+  double* blk = rx + H * NR;            // 6 blocks
 
   const double* cand_q = p.cand_q + (size_t)r * (H + 2) * NQ;
   const double* cand_u = p.cand_u + (size_t)r * H * NU;
   const double* cand_nu = p.cand_nu + (size_t)r * H * ND;
-  for (int e = tid; e < (H + 2) * NQ; e += THREADS) cq[e] = cand_q[e];
-  for (int e = tid; e < H * NU; e += THREADS) cu[e] = cand_u[e];
-  for (int e = tid; e < H * ND; e += THREADS) cnu[e] = cand_nu[e];
-  for (int t = 0; t < H; ++t) {
-    const double* src = p.dz + ((size_t)t * R + r) * (ND * NCOL);
-    for (int e = tid; e < ND * NCOL; e += THREADS) DZ[t * ND * NCOL + e] = src[e];
-  }
-  for (int e = tid; e < H * NR; e += THREADS) {
-    const int t = e / NR, c = e % NR;
-    qi[e] = 1.0 / (c < NU ? p.obj_u[t * NU + c] : p.obj_q[t * NQ + c - NU]);
-  }
-  __syncthreads();
+  for (int e = lane; e < (H + 2) * NQ; e += 32) cq[e] = cand_q[e];
+  for (int e = lane; e < H * NU; e += 32) cu[e] = cand_u[e];
+  for (int e = lane; e < H * ND; e += 32) cnu[e] = cand_nu[e];
+  __syncwarp();
+  // δz of stage t: element (row a, column c) — the δq0 | δq1 | δu1 views (implicit_dynamics.jl:82-86)
+  auto DZ = [&](int t, int c, int a) -> double { return p.dz[(((size_t)t * R + r) * NCOL + c) * ND + a]; };
+  auto QIu = [&](int t, int k) -> double { return 1.0 / p.obj_u[t * NU + k]; };
+  auto QIq = [&](int t, int k) -> double { return 1.0 / p.obj_q[t * NQ + k]; };
+
   // d_t = z*_t[1:nq] − q_{t+2}   (implicit_dynamics.jl:180-182)
-  for (int e = tid; e < H * ND; e += THREADS) {
+  for (int e = lane; e < H * ND; e += 32) {
     const int t = e / ND, i = e % ND;
     dv[e] = p.z[((size_t)t * R + r) * NZ + i] - cq[(t + 2) * NQ + i];
   }
   // residual!  (newton_residual.jl:113-138), primal rows
-  for (int e = tid; e < H * NR; e += THREADS) {
+  for (int e = lane; e < H * NR; e += 32) {
     const int t = e / NR, c = e % NR;
     double acc;
     if (c < NU) {  // u_t:  obj.u (u − u_ref) + δu1_tᵀ ν_t
       acc = p.obj_u[t * NU + c] * (cu[t * NU + c] - p.ref_u[t * NU + c]);
-      const double* col = DZ + t * ND * NCOL + (2 * NQ + c) * ND;
-      for (int i = 0; i < ND; ++i) acc = fma(col[i], cnu[t * ND + i], acc);
+      for (int i = 0; i < ND; ++i) acc = fma(DZ(t, 2 * NQ + c, i), cnu[t * ND + i], acc);
     } else {  // q_{t+2}: obj.q (q − q_ref) − ν_t + δq1_{t+1}ᵀ ν_{t+1} + δq0_{t+2}ᵀ ν_{t+2}
       const int k = c - NU;
       acc = p.obj_q[t * NQ + k] * (cq[(t + 2) * NQ + k] - p.ref_q[(t + 2) * NQ + k]) - cnu[t * ND + k];
-      if (t + 1 < H) {
-        const double* col = DZ + (t + 1) * ND * NCOL + (NQ + k) * ND;
-        for (int i = 0; i < ND; ++i) acc = fma(col[i], cnu[(t + 1) * ND + i], acc);
-      }
-      if (t + 2 < H) {
-        const double* col = DZ + (t + 2) * ND * NCOL + (k)*ND;
-        for (int i = 0; i < ND; ++i) acc = fma(col[i], cnu[(t + 2) * ND + i], acc);
-      }
+      if (t + 1 < H)
+        for (int i = 0; i < ND; ++i) acc = fma(DZ(t + 1, NQ + k, i), cnu[(t + 1) * ND + i], acc);
+      if (t + 2 < H)
+        for (int i = 0; i < ND; ++i) acc = fma(DZ(t + 2, k, i), cnu[(t + 2) * ND + i], acc);
     }
     rx[e] = acc;
   }
-  __syncthreads();
+  __syncwarp();
   // r_cand = ‖res‖₁  (newton.jl:198, 241) — fixed-order reduction: deterministic
-  {
-    double part = 0.0;
-    for (int e = tid; e < H * NR; e += THREADS) part += fabs(rx[e]);
-    for (int e = tid; e < H * ND; e += THREADS) part += fabs(dv[e]);
+  double r_cand = 0.0;
+  for (int e = lane; e < H * NR; e += 32) r_cand += fabs(rx[e]);
+  for (int e = lane; e < H * ND; e += 32) r_cand += fabs(dv[e]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((tid & 31) == 0) red[tid >> 5] = part;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    double r_cand = 0.0;
-    for (int wgt = 0; wgt < THREADS / 32; ++wgt) r_cand += red[wgt];
-    const int len = H * (NR + ND);
-    double r_norm = p.r_norm[r], alpha = p.alpha[r], beta = p.beta[r];
-    int ls = p.ls_it[r], l = p.newton_it[r];
-    p.sweeps[r] += 1;
-    int action;
-    bool accept = false;
-    if (phase == NP_INIT) {
-      r_norm = r_cand;
-      action = 1;
+  for (int o = 16; o > 0; o >>= 1) r_cand += __shfl_xor_sync(FULLM, r_cand, o);
+
+  // ---- state machine (uniform across the warp: every lane evaluates the same scalars) ----
+  const int len = H * (NR + ND);
+  double r_norm = p.r_norm[r], alpha = p.alpha[r], beta = p.beta[r];
+  int ls = p.ls_it[r], l = p.newton_it[r];
+  int action;  // 0: re-evaluate at a smaller α, 1: solve for a new direction, 2: finished
+  bool accept = false;
+  if (phase == NP_INIT) {
+    r_norm = r_cand;
+    action = 1;
+  } else {
+    if (r_cand * r_cand >= (1.0 - 0.001 * alpha) * r_norm * r_norm) {  // newton.jl:245
+      alpha *= 0.5;
+      ls += 1;
+      if (ls > 6) accept = true;  // the halved α is applied without being evaluated (newton.jl:249-251, 273)
+      action = accept ? 1 : 0;
     } else {
-      if (r_cand * r_cand >= (1.0 - 0.001 * alpha) * r_norm * r_norm) {  // newton.jl:245
-        alpha *= 0.5;
-        ls += 1;
-        if (ls > 6) accept = true;  // the halved α is applied without being evaluated (newton.jl:249-251, 273)
-        action = accept ? 1 : 0;
-      } else {
-        accept = true;
-        action = 1;
-      }
-      if (accept) {
-        r_norm = r_cand;
-        beta = (ls > 6) ? fmin(beta * 1.3, 1.0e2) : fmax(1.0e1, beta / 1.3);  // newton.jl:280
-        l += 1;
-      }
+      accept = true;
+      action = 1;
     }
-    if (action == 1 && (r_norm / (double)len < p.r_tol || l >= p.max_iter)) action = 2;  // newton.jl:202-206
-    s_action = action | (accept ? 4 : 0);
-    s_alpha = alpha;
+    if (accept) {
+      r_norm = r_cand;
+      beta = (ls > 6) ? fmin(beta * 1.3, 1.0e2) : fmax(1.0e1, beta / 1.3);  // newton.jl:280
+      l += 1;
+    }
+  }
+  if (action == 1 && (r_norm / (double)len < p.r_tol || l >= p.max_iter)) action = 2;  // newton.jl:202-206
+  if (lane == 0) {
+    p.sweeps[r] += 1;
     p.r_norm[r] = r_norm;
     p.alpha[r] = alpha;
     p.beta[r] = beta;
     p.ls_it[r] = ls;
     p.newton_it[r] = l;
   }
-  __syncthreads();
-  const int action = s_action & 3;
-  const bool accept = (s_action & 4) != 0;
-  const double alpha_acc = s_alpha;
+  const double alpha_acc = alpha;
   double* traj_q = p.traj_q + (size_t)r * (H + 2) * NQ;
   double* traj_u = p.traj_u + (size_t)r * H * NU;
   double* nu = p.nu + (size_t)r * H * ND;
@@ -202,24 +185,18 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
   double* cnu_g = p.cand_nu + (size_t)r * H * ND;
 
   if (accept) {  // update_traj!(traj, traj, ν, ν, Δ, α)  (newton.jl:273)
-    for (int e = tid; e < H * NQ; e += THREADS) {
+    for (int e = lane; e < H * NQ; e += 32) {
       const int t = e / NQ, k = e % NQ;
       traj_q[(t + 2) * NQ + k] -= alpha_acc * delta[t * (NR + ND) + NU + k];
     }
-    for (int e = tid; e < H * NU; e += THREADS) {
-      const int t = e / NU, k = e % NU;
-      traj_u[e] -= alpha_acc * delta[t * (NR + ND) + k];
-    }
-    for (int e = tid; e < H * ND; e += THREADS) {
-      const int t = e / ND, k = e % ND;
-      nu[e] -= alpha_acc * delta[t * (NR + ND) + NR + k];
-    }
-    __syncthreads();
+    for (int e = lane; e < H * NU; e += 32) traj_u[e] -= alpha_acc * delta[(e / NU) * (NR + ND) + e % NU];
+    for (int e = lane; e < H * ND; e += 32) nu[e] -= alpha_acc * delta[(e / ND) * (NR + ND) + NR + e % ND];
+    __syncwarp();
   }
 
   if (action == 2) {  // finished: switch the rollout's subproblems off
-    for (int t = tid; t < H; t += THREADS) p.knot[(size_t)t * R + r] = -1;
-    if (tid == 0) {
+    for (int t = lane; t < H; t += 32) p.knot[(size_t)t * R + r] = -1;
+    if (lane == 0) {
       p.phase[r] = NP_DONE;
       atomicSub(p.n_active, 1);
     }
@@ -229,115 +206,158 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
   double alpha_next;
   if (action == 1) {
     // ---------------- jacobian! + linear_solve! through the dual Schur complement ----------------
-    const double rho = (double)H * p.beta[r] * p.kappa;
-    for (int e = tid; e < LDB * N; e += THREADS) Yb[e] = 0.0;
-    for (int e = tid; e < H * NR; e += THREADS) vx[e] = qi[e] * rx[e];
-    __syncthreads();
-    // Y blocks (t,t), (t,t−1), (t,t−2); element (a,b) of block (t,s) lives at row t·nd+a, column s·nd+b
-    const int per = 3 * ND * ND;
-    for (int e = tid; e < H * per; e += THREADS) {
-      const int t = e / per, rem = e % per, which = rem / (ND * ND), a = (rem % (ND * ND)) % ND, b = (rem % (ND * ND)) / ND;
-      const int s = t - which;
-      if (s < 0) continue;
-      const int i = t * ND + a, j = s * ND + b;
-      if (i < j) continue;  // lower triangle only
-      const double* Zt = DZ + t * ND * NCOL;
-      double acc = 0.0;
-      if (which == 0) {
-        for (int k = 0; k < NU; ++k) acc = fma(Zt[(2 * NQ + k) * ND + a] * qi[t * NR + k], Zt[(2 * NQ + k) * ND + b], acc);
-        if (a == b) acc += qi[t * NR + NU + a] + rho;
-        if (t >= 1)
-          for (int k = 0; k < NQ; ++k)
-            acc = fma(Zt[(NQ + k) * ND + a] * qi[(t - 1) * NR + NU + k], Zt[(NQ + k) * ND + b], acc);
-        if (t >= 2)
-          for (int k = 0; k < NQ; ++k) acc = fma(Zt[k * ND + a] * qi[(t - 2) * NR + NU + k], Zt[k * ND + b], acc);
-      } else if (which == 1) {
-        // shared variables of rows t and t−1: q_{t+1} (δq1_t vs −I) and q_t (δq0_t vs δq1_{t−1})
-        acc = -Zt[(NQ + b) * ND + a] * qi[(t - 1) * NR + NU + b];
-        if (t >= 2) {
-          const double* Zs = DZ + (t - 1) * ND * NCOL;
-          for (int k = 0; k < NQ; ++k) acc = fma(Zt[k * ND + a] * qi[(t - 2) * NR + NU + k], Zs[(NQ + k) * ND + b], acc);
-        }
-      } else {
-        acc = -Zt[b * ND + a] * qi[(t - 2) * NR + NU + b];  // q_t: δq0_t vs −I of row t−2
-      }
-      Yb[(i - j) + j * LDB] = acc;
-    }
+    const double rho = (double)H * beta * p.kappa;
+    double* Ls = lscratch + (size_t)r * SM::l_doubles(H);
     // g = C Q⁻¹ r_x − r_ν
-    for (int e = tid; e < H * ND; e += THREADS) {
+    for (int e = lane; e < H * ND; e += 32) {
       const int t = e / ND, a = e % ND;
-      const double* Zt = DZ + t * ND * NCOL;
-      double acc = -vx[t * NR + NU + a] - dv[e];
-      for (int k = 0; k < NU; ++k) acc = fma(Zt[(2 * NQ + k) * ND + a], vx[t * NR + k], acc);
+      double acc = -rx[t * NR + NU + a] * QIq(t, a) - dv[e];
+      for (int k = 0; k < NU; ++k) acc = fma(DZ(t, 2 * NQ + k, a), rx[t * NR + k] * QIu(t, k), acc);
       if (t >= 1)
-        for (int k = 0; k < NQ; ++k) acc = fma(Zt[(NQ + k) * ND + a], vx[(t - 1) * NR + NU + k], acc);
+        for (int k = 0; k < NQ; ++k) acc = fma(DZ(t, NQ + k, a), rx[(t - 1) * NR + NU + k] * QIq(t - 1, k), acc);
       if (t >= 2)
-        for (int k = 0; k < NQ; ++k) acc = fma(Zt[k * ND + a], vx[(t - 2) * NR + NU + k], acc);
+        for (int k = 0; k < NQ; ++k) acc = fma(DZ(t, k, a), rx[(t - 2) * NR + NU + k] * QIq(t - 2, k), acc);
       gv[e] = acc;
     }
-    __syncthreads();
-    // banded Cholesky Y = L Lᵀ (right-looking, in place)
-    for (int j = 0; j < N; ++j) {
-      const int m = min(KD, N - 1 - j);
-      const double dj = sqrt(Yb[j * LDB]);
-      __syncthreads();
-      if (tid == 0) Yb[j * LDB] = dj;
-      const double inv = 1.0 / dj;
-      for (int i = 1 + tid; i <= m; i += THREADS) Yb[i + j * LDB] *= inv;
-      __syncthreads();
-      for (int e = tid; e < m * m; e += THREADS) {
-        const int i1 = 1 + e % m, i2 = 1 + e / m;
-        if (i2 >= i1) Yb[(i2 - i1) + (j + i1) * LDB] = fma(-Yb[i2 + j * LDB], Yb[i1 + j * LDB], Yb[(i2 - i1) + (j + i1) * LDB]);
+    __syncwarp();
+    // sliding window of blocks (column-major ND×ND): working column A0, A1, A2 and the factor blocks
+    // P1 = L_{t,t−1}, P2 = L_{t+1,t−1}, Q2 = L_{t,t−2} of the two previous block columns
+    double *A0 = blk, *A1 = blk + BS, *A2 = blk + 2 * BS, *P1 = blk + 3 * BS, *P2 = blk + 4 * BS, *Q2 = blk + 5 * BS;
+    for (int t = 0; t < H; ++t) {
+      // ---- assemble block column t of Y minus the pending Cholesky updates ----
+      for (int e = lane; e < BS; e += 32) {
+        const int a = e % ND, b = e / ND;
+        // (t,t): δu1 Qu⁻¹ δu1ᵀ + Qq_t⁻¹ + δq1 Qq_{t−1}⁻¹ δq1ᵀ + δq0 Qq_{t−2}⁻¹ δq0ᵀ + ρI   (lower triangle)
+        double acc = 0.0;
+        if (a >= b) {
+          for (int k = 0; k < NU; ++k) acc = fma(DZ(t, 2 * NQ + k, a) * QIu(t, k), DZ(t, 2 * NQ + k, b), acc);
+          if (a == b) acc += QIq(t, a) + rho;
+          if (t >= 1) {
+            for (int k = 0; k < NQ; ++k) acc = fma(DZ(t, NQ + k, a) * QIq(t - 1, k), DZ(t, NQ + k, b), acc);
+            for (int k = 0; k < ND; ++k) acc = fma(-P1[a + k * ND], P1[b + k * ND], acc);
+          }
+          if (t >= 2) {
+            for (int k = 0; k < NQ; ++k) acc = fma(DZ(t, k, a) * QIq(t - 2, k), DZ(t, k, b), acc);
+            for (int k = 0; k < ND; ++k) acc = fma(-Q2[a + k * ND], Q2[b + k * ND], acc);
+          }
+        }
+        A0[e] = acc;
+        // (t+1,t): −δq1_{t+1} Qq_t⁻¹ + δq0_{t+1} Qq_{t−1}⁻¹ δq1_tᵀ  − L_{t+1,t−1} L_{t,t−1}ᵀ
+        if (t + 1 < H) {
+          double c1 = -DZ(t + 1, NQ + b, a) * QIq(t, b);
+          if (t >= 1) {
+            for (int k = 0; k < NQ; ++k) c1 = fma(DZ(t + 1, k, a) * QIq(t - 1, k), DZ(t, NQ + k, b), c1);
+            for (int k = 0; k < ND; ++k) c1 = fma(-P2[a + k * ND], P1[b + k * ND], c1);
+          }
+          A1[e] = c1;
+        }
+        // (t+2,t): −δq0_{t+2} Qq_t⁻¹
+        if (t + 2 < H) A2[e] = -DZ(t + 2, b, a) * QIq(t, b);
       }
-      __syncthreads();
+      __syncwarp();
+      // ---- potrf: A0 = L Lᵀ in place (lane = row) ----
+      for (int j = 0; j < ND; ++j) {
+        const double djj = sqrt(A0[j + j * ND]);
+        const double inv = 1.0 / djj;
+        __syncwarp();
+        if (lane == j) A0[j + j * ND] = djj;
+        if (lane > j && lane < ND) A0[lane + j * ND] *= inv;
+        __syncwarp();
+        if (lane > j && lane < ND) {
+          const double laj = A0[lane + j * ND];
+          for (int c = j + 1; c <= lane; ++c) A0[lane + c * ND] = fma(-laj, A0[c + j * ND], A0[lane + c * ND]);
+        }
+        __syncwarp();
+      }
+      // ---- trsm: A1 ← A1 L⁻ᵀ, A2 ← A2 L⁻ᵀ (lane = row of [A1; A2]); forward substitution for y_t ----
+      {
+        const int nrows = (t + 1 < H ? ND : 0) + (t + 2 < H ? ND : 0);
+        if (lane < nrows) {
+          double* X = (lane < ND) ? (A1 + lane) : (A2 + lane - ND);
+          for (int c = 0; c < ND; ++c) {
+            double s = X[c * ND];
+            for (int k = 0; k < c; ++k) s = fma(-X[k * ND], A0[c + k * ND], s);
+            X[c * ND] = s / A0[c + c * ND];
+          }
+        }
+        __syncwarp();
+        // y_t = L_tt⁻¹ (g_t − L_{t,t−1} y_{t−1} − L_{t,t−2} y_{t−2})
+        if (lane < ND) {
+          double s = gv[t * ND + lane];
+          if (t >= 1)
+            for (int k = 0; k < ND; ++k) s = fma(-P1[lane + k * ND], gv[(t - 1) * ND + k], s);
+          if (t >= 2)
+            for (int k = 0; k < ND; ++k) s = fma(-Q2[lane + k * ND], gv[(t - 2) * ND + k], s);
+          gv[t * ND + lane] = s;
+        }
+        __syncwarp();
+        for (int c = 0; c < ND; ++c) {
+          const double yc = gv[t * ND + c] / A0[c + c * ND];
+          __syncwarp();
+          if (lane == c) gv[t * ND + c] = yc;
+          if (lane > c && lane < ND) gv[t * ND + lane] = fma(-A0[lane + c * ND], yc, gv[t * ND + lane]);
+          __syncwarp();
+        }
+      }
+      // ---- keep the block column for the backward pass, slide the window ----
+      for (int e = lane; e < BS; e += 32) {
+        Ls[(size_t)(3 * t) * BS + e] = A0[e];
+        if (t + 1 < H) Ls[(size_t)(3 * t + 1) * BS + e] = A1[e];
+        if (t + 2 < H) Ls[(size_t)(3 * t + 2) * BS + e] = A2[e];
+      }
+      __syncwarp();
+      double* oldQ2 = Q2;
+      Q2 = P2;     // L_{t+1,t−1} is L_{t',t'−2} of the next column t' = t+1
+      P2 = A2;     // L_{t+2,t}   →  L_{t'+1,t'−1}
+      double* oldP1 = P1;
+      P1 = A1;     // L_{t+1,t}   →  L_{t',t'−1}
+      A1 = oldP1;
+      A2 = oldQ2;
     }
-    // L y = g, Lᵀ Δν = y  (one warp; the band fits 32 lanes + 1)
-    if (tid < 32) {
-      for (int j = 0; j < N; ++j) {
-        const int m = min(KD, N - 1 - j);
-        const double yj = gv[j] / Yb[j * LDB];
-        __syncwarp();
-        if (tid == 0) gv[j] = yj;
-        for (int i = 1 + tid; i <= m; i += 32) gv[j + i] = fma(-Yb[i + j * LDB], yj, gv[j + i]);
-        __syncwarp();
+    // ---- backward: Δν_t = L_tt⁻ᵀ (y_t − L_{t+1,t}ᵀ Δν_{t+1} − L_{t+2,t}ᵀ Δν_{t+2}) ----
+    for (int t = H - 1; t >= 0; --t) {
+      const double* L0 = Ls + (size_t)(3 * t) * BS;
+      const double* L1 = L0 + BS;
+      const double* L2 = L0 + 2 * BS;
+      for (int e = lane; e < BS; e += 32) A0[e] = L0[e];
+      if (lane < ND) {
+        double s = gv[t * ND + lane];
+        if (t + 1 < H)
+          for (int k = 0; k < ND; ++k) s = fma(-L1[k + lane * ND], gv[(t + 1) * ND + k], s);
+        if (t + 2 < H)
+          for (int k = 0; k < ND; ++k) s = fma(-L2[k + lane * ND], gv[(t + 2) * ND + k], s);
+        gv[t * ND + lane] = s;
       }
-      for (int j = N - 1; j >= 0; --j) {
-        const int m = min(KD, N - 1 - j);
-        double part = 0.0;
-        for (int i = 1 + tid; i <= m; i += 32) part = fma(Yb[i + j * LDB], gv[j + i], part);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      __syncwarp();
+      for (int c = ND - 1; c >= 0; --c) {
+        const double xc = gv[t * ND + c] / A0[c + c * ND];
         __syncwarp();
-        if (tid == 0) gv[j] = (gv[j] - part) / Yb[j * LDB];
+        if (lane == c) gv[t * ND + c] = xc;
+        if (lane < c) gv[t * ND + lane] = fma(-A0[c + lane * ND], xc, gv[t * ND + lane]);
         __syncwarp();
       }
     }
-    __syncthreads();
     // Δx = Q⁻¹ (r_x − Cᵀ Δν);  Δ = [Δu, Δq, Δν] per stage
-    for (int e = tid; e < H * NR; e += THREADS) {
+    for (int e = lane; e < H * NR; e += 32) {
       const int t = e / NR, c = e % NR;
       double acc = rx[e];
       if (c < NU) {
-        const double* col = DZ + t * ND * NCOL + (2 * NQ + c) * ND;
-        for (int i = 0; i < ND; ++i) acc = fma(-col[i], gv[t * ND + i], acc);
+        for (int i = 0; i < ND; ++i) acc = fma(-DZ(t, 2 * NQ + c, i), gv[t * ND + i], acc);
+        delta[t * (NR + ND) + c] = QIu(t, c) * acc;
       } else {
         const int k = c - NU;
         acc += gv[t * ND + k];
-        if (t + 1 < H) {
-          const double* col = DZ + (t + 1) * ND * NCOL + (NQ + k) * ND;
-          for (int i = 0; i < ND; ++i) acc = fma(-col[i], gv[(t + 1) * ND + i], acc);
-        }
-        if (t + 2 < H) {
-          const double* col = DZ + (t + 2) * ND * NCOL + k * ND;
-          for (int i = 0; i < ND; ++i) acc = fma(-col[i], gv[(t + 2) * ND + i], acc);
-        }
+        if (t + 1 < H)
+          for (int i = 0; i < ND; ++i) acc = fma(-DZ(t + 1, NQ + k, i), gv[(t + 1) * ND + i], acc);
+        if (t + 2 < H)
+          for (int i = 0; i < ND; ++i) acc = fma(-DZ(t + 2, k, i), gv[(t + 2) * ND + i], acc);
+        delta[t * (NR + ND) + c] = QIq(t, k) * acc;
       }
-      delta[t * (NR + ND) + c] = qi[e] * acc;
     }
-    for (int e = tid; e < H * ND; e += THREADS) delta[(e / ND) * (NR + ND) + NR + e % ND] = gv[e];
-    __syncthreads();
+    for (int e = lane; e < H * ND; e += 32) delta[(e / ND) * (NR + ND) + NR + e % ND] = gv[e];
+    __syncwarp();
     alpha_next = 1.0;
-    if (tid == 0) {
+    if (lane == 0) {
       p.alpha[r] = 1.0;
       p.ls_it[r] = 0;
       p.phase[r] = NP_LS;
@@ -347,18 +367,18 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
   }
 
   // candidate = traj − α Δ  (update_traj!, newton_residual.jl:160-176), then the next sweep's inputs
-  for (int e = tid; e < 2 * NQ; e += THREADS) cq[e] = traj_q[e];
-  for (int e = tid; e < H * NQ; e += THREADS) {
+  for (int e = lane; e < 2 * NQ; e += 32) cq[e] = traj_q[e];
+  for (int e = lane; e < H * NQ; e += 32) {
     const int t = e / NQ, k = e % NQ;
     cq[(t + 2) * NQ + k] = traj_q[(t + 2) * NQ + k] - alpha_next * delta[t * (NR + ND) + NU + k];
   }
-  for (int e = tid; e < H * NU; e += THREADS) cu[e] = traj_u[e] - alpha_next * delta[(e / NU) * (NR + ND) + e % NU];
-  for (int e = tid; e < H * ND; e += THREADS) cnu_g[e] = nu[e] - alpha_next * delta[(e / ND) * (NR + ND) + NR + e % ND];
-  __syncthreads();
-  for (int e = tid; e < (H + 2) * NQ; e += THREADS) cq_g[e] = cq[e];
-  for (int e = tid; e < H * NU; e += THREADS) cu_g[e] = cu[e];
+  for (int e = lane; e < H * NU; e += 32) cu[e] = traj_u[e] - alpha_next * delta[(e / NU) * (NR + ND) + e % NU];
+  for (int e = lane; e < H * ND; e += 32) cnu_g[e] = nu[e] - alpha_next * delta[(e / ND) * (NR + ND) + NR + e % ND];
+  __syncwarp();
+  for (int e = lane; e < (H + 2) * NQ; e += 32) cq_g[e] = cq[e];
+  for (int e = lane; e < H * NU; e += 32) cu_g[e] = cu[e];
   // θ_t = [q_t; q_{t+1}; u_t; w_t; μ; h]  (update_θ!, trajectory.jl:67-82), cold start q2 = q_{t+2}
-  for (int e = tid; e < H * NTH; e += THREADS) {
+  for (int e = lane; e < H * NTH; e += 32) {
     const int t = e / NTH, c = e % NTH;
     double v;
     if (c < NQ) v = cq[t * NQ + c];
@@ -369,7 +389,7 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
     else v = p.h;
     p.theta[((size_t)t * R + r) * NTH + c] = v;
   }
-  for (int e = tid; e < H * NQ; e += THREADS) {
+  for (int e = lane; e < H * NQ; e += 32) {
     const int t = e / NQ, k = e % NQ;
     p.q2[((size_t)t * R + r) * NQ + k] = cq[(t + 2) * NQ + k];
   }

@@ -21,10 +21,11 @@ struct ModelEntry {
   cudaError_t (*occupancy)(int* blocks_per_sm);
   // device Newton (:configuration instances only, else null)
   cudaError_t (*newton_reset)(const NewtonParams& p, const double* q0, const double* q1, int warm, cudaStream_t s);
-  cudaError_t (*newton_step)(const NewtonParams& p, cudaStream_t s);
+  cudaError_t (*newton_step)(const NewtonParams& p, double* lscratch, cudaStream_t s);
+  size_t (*newton_scratch)(int H);  // doubles of global scratch per rollout
 };
 
-constexpr int NEWTON_THREADS = 128;
+constexpr int NEWTON_THREADS = 32 * NEWTON_WARPS;
 
 template <class D>
 cudaError_t launch_newton_reset(const NewtonParams& p, const double* q0, const double* q1, int warm, cudaStream_t s) {
@@ -33,8 +34,8 @@ cudaError_t launch_newton_reset(const NewtonParams& p, const double* q0, const d
 }
 
 template <class D>
-cudaError_t launch_newton_step(const NewtonParams& p, cudaStream_t s) {
-  const size_t bytes = (size_t)NewtonSmem<D>::doubles(p.H) * sizeof(double);
+cudaError_t launch_newton_step(const NewtonParams& p, double* lscratch, cudaStream_t s) {
+  const size_t bytes = (size_t)NewtonSmem<D>::per_warp(p.H) * NEWTON_WARPS * sizeof(double);
   static size_t configured = 0;
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(newton_step_kernel<D, NEWTON_THREADS>,
@@ -42,8 +43,14 @@ cudaError_t launch_newton_step(const NewtonParams& p, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = bytes;
   }
-  newton_step_kernel<D, NEWTON_THREADS><<<p.R, NEWTON_THREADS, bytes, s>>>(p);
+  const int grid = (p.R + NEWTON_WARPS - 1) / NEWTON_WARPS;
+  newton_step_kernel<D, NEWTON_THREADS><<<grid, NEWTON_THREADS, bytes, s>>>(p, lscratch);
   return cudaGetLastError();
+}
+
+template <class D>
+size_t newton_scratch_doubles(int H) {
+  return NewtonSmem<D>::l_doubles(H);
 }
 
 constexpr int IP_THREADS = 256;
@@ -103,9 +110,9 @@ CIMPC_FOR_EACH_MODEL(CIMPC_DECLARE_ENTRY)
     using D1 = Dims<nq, nu, nw, nc, nb, 1>;                                                       \
     static const ModelEntry e[2] = {                                                              \
         {#name_, {nq, nu, nw, nc, nb, 0}, layout_of<D0>(), &launch_ip<D0>, &occupancy_ip<D0>,     \
-         &launch_newton_reset<D0>, &launch_newton_step<D0>},                                      \
+         &launch_newton_reset<D0>, &launch_newton_step<D0>, &newton_scratch_doubles<D0>},         \
         {#name_, {nq, nu, nw, nc, nb, 1}, layout_of<D1>(), &launch_ip<D1>, &occupancy_ip<D1>,     \
-         nullptr, nullptr}};                                                                      \
+         nullptr, nullptr, nullptr}};                                                             \
     *count = 2;                                                                                   \
     return e;                                                                                     \
   }

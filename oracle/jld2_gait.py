@@ -217,3 +217,29 @@ def load_split_traj_alt(path: str) -> dict:
     out["mu"] = float(np.asarray(f["μm"]).reshape(-1)[0])
     out["h"] = float(np.asarray(f["hm"]).reshape(-1)[0])
     return out
+
+
+def load_joint_traj(path: str) -> dict:
+    """`get_trajectory(..., load_type = :joint_traj)` (trajectory.jl:180-181): the file holds ONE serialized
+    `ContactTraj` struct under "traj" (scalar dataset, committed compound datatype, compact layout):
+    H::Int64, h::Float64, then 15 object references κ, q, u, w, γ, b, z, θ, iq0, iq1, iu1, iw1, iq2, iγ1, ib1
+    (field order of `struct ContactTraj`, trajectory.jl:1-19).  Returns the arrays needed downstream."""
+    f = JLD2File(path)
+    payload = None
+    for (mtype, _fl), pl in f._messages_with_flags(f.links["traj"]):
+        if mtype == 8:
+            if pl[1] != 0:
+                raise ValueError("expected a compact layout for the ContactTraj struct")
+            n = struct.unpack_from("<H", pl, 2)[0]
+            payload = pl[4:4 + n]
+    if payload is None or len(payload) != 16 + 15 * 8:
+        raise ValueError("unexpected ContactTraj layout")
+    H, = struct.unpack_from("<q", payload, 0)
+    h, = struct.unpack_from("<d", payload, 8)
+    refs = struct.unpack_from("<15Q", payload, 16)
+    out = {"H": int(H), "h": float(h)}
+    for name, ref in zip(("kappa", "q", "u", "w", "gamma", "b", "z", "theta"), refs[:8]):
+        v = f.read(int(ref))
+        out[name] = np.stack([np.asarray(x, dtype=np.float64) for x in v]) if isinstance(v, list) else np.asarray(v)
+    assert out["q"].shape[0] == H + 2 and out["theta"].shape[0] == H
+    return out

@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-from .jld2_gait import load_split_traj_alt
+from .jld2_gait import load_joint_traj, load_split_traj_alt
 from .linearized import linearized_step
 from .residual import get_residual
 from .trajectory import trajectory_from_gait
@@ -36,8 +36,28 @@ CONFIGS = {
 }
 
 
+def hopper():
+    """examples/hopper/flat.jl:15-27: `gait_forward.jld2` is a serialized ContactTraj (:joint_traj), κ_mpc = 2e-4."""
+    tr = load_joint_traj(os.path.join(REF, "hopper_2D/gaits/gait_forward.jld2"))
+    res = get_residual("hopper_2D")
+    H, kappa = tr["H"], 2.0e-4
+    nq, nc, nb = res.model.nq, res.model.nc, res.model.nb
+    z, th = tr["z"], tr["theta"]
+    gait = dict(q=tr["q"], u=tr["u"], gamma=tr["gamma"], b=tr["b"], psi=z[:, nq + nc + nb:nq + 2 * nc + nb],
+                eta=z[:, nq + 3 * nc + nb:nq + 3 * nc + 2 * nb], mu=float(th[0, -2]), h=tr["h"], w=tr["w"])
+    np.savez_compressed(os.path.join(OUT, "hopper_2D_gait.npz"), **gait)
+    r0 = np.zeros((H, res.idx.nz)); rz0 = np.zeros((H, res.idx.nz, res.idx.nz)); rth0 = np.zeros((H, res.idx.nz, res.idx.ntheta))
+    for t in range(H):
+        r0[t], rz0[t], rth0[t] = linearized_step(res, z[t], th[t], kappa)
+    np.savez_compressed(os.path.join(OUT, "hopper_2D_lin.npz"), z0=z, th0=th, r0=r0, rz0=rz0, rth0=rth0, kappa=kappa)
+    worst = max(np.linalg.norm(res.r(z[t], th[t], 0.0)) for t in range(H))
+    print("hopper_2D H =", H, "max ||r(z_t, θ_t, 0)|| =", worst)
+
+
 def main(robots=None):
     os.makedirs(OUT, exist_ok=True)
+    if not robots or "hopper_2D" in robots:
+        hopper()
     for name, (gait_file, kappa) in CONFIGS.items():
         if robots and name not in robots:
             continue

@@ -34,6 +34,9 @@ CONFIGS = [
     # examples/centroidal_quadruped/flat_trot.jl:31-62
     ("centroidal_quadruped", "configuration", dict(r_tol=1e-8, kappa_tol=2e-4)),
     ("centroidal_quadruped", "configurationforce", dict(r_tol=1e-8, kappa_tol=2e-4)),
+    # examples/hopper/flat.jl:24-48 (4 lanes per subproblem, 8 subproblems per warp)
+    ("hopper_2D", "configuration", dict(r_tol=1e-8, kappa_tol=2e-4)),
+    ("hopper_2D", "configurationforce", dict(r_tol=1e-8, kappa_tol=2e-4)),
 ]
 
 
@@ -86,7 +89,7 @@ def test_strict_parity_every_problem(cuda_device, robot, mode, kw):
     assert np.array_equal(it[sub][ok], itn[ok]) and ezn[ok].max() <= 1e-9 and edzn[ok].max() <= 1e-8
 
 
-@pytest.mark.parametrize("robot,mode,kw", CONFIGS[:4] + CONFIGS[5:6])
+@pytest.mark.parametrize("robot,mode,kw", CONFIGS[:4] + CONFIGS[5:6] + CONFIGS[7:8])
 def test_reference_settings_parity(cuda_device, robot, mode, kw):
     import cimpc_b200 as cb
     lin, gait = load_lin(robot), load_gait(robot)

@@ -187,3 +187,50 @@ def test_c_restatement_matches_numpy_oracle():
             floors[robot, solver] = ez
     # the MGS floor really is orders of magnitude above the LU floor on the ill-conditioned robot
     assert floors["flamingo", "mgs"] > 100 * floors["flamingo", "lu"]
+
+
+def test_hopper_single_policy_call():
+    """BASELINE config 1 — hopper flat (examples/hopper/flat.jl:15-51): ONE `policy` call of the CI-MPC on
+    the CPU (plumbing / correctness, no GPU): ImplicitTrajectory from the shipped gait (a serialized
+    ContactTraj, :joint_traj), H_mpc = 10, κ = 2e-4, IP r_tol = 1e-8 / κ_tol = 2e-4, Newton r_tol = 3e-4,
+    max_iter = 5, then rot_n_stride! / update_window! exactly as policy.jl:119-131."""
+    from oracle.c_oracle import COracle
+    from oracle.models import get_model
+    from oracle.newton import (Newton, NewtonOptions, TrackingObjective, get_stride, rot_n_stride, update_window)
+    from oracle.trajectory import ContactTraj
+    robot = "hopper_2D"
+    m = get_model(robot)
+    lin, gait = load_lin(robot), load_gait(robot)
+    H_ref, H = lin["z0"].shape[0], 10
+    ref = ContactTraj(m, H_ref, gait["h"])
+    ref.q[:] = gait["q"]; ref.u[:] = gait["u"]; ref.w[:] = gait["w"]; ref.gamma[:] = gait["gamma"]; ref.b[:] = gait["b"]
+    ref.z[:] = lin["z0"]; ref.theta[:] = lin["th0"]
+    # the implicit dynamics reproduce the gait (the hopper analogue of test/controller/implicit_dynamics.jl:24)
+    co = COracle(*SIZES[robot], lin, mode="configuration", solver="mgs")
+    ipo = IPOptions(r_tol=1e-8, kappa_tol=2e-4, undercut=5.0, diff_sol=True)
+    z, dz, st, it = co.solve(np.arange(H_ref, dtype=np.int32), ref.theta, ref.q[2:], ipo)
+    assert st.all() and np.abs(z[:, :m.nq] - ref.q[2:]).max() < 1e-2
+
+    def dyn(window, traj):
+        knot = np.array(window[:H], dtype=np.int32)
+        zz, dzz, stt, _ = co.solve(knot, traj.theta[:H], traj.q[2:H + 2], ipo)
+        assert stt.all()
+        nq = m.nq
+        return zz[:, :nq] - traj.q[2:H + 2], dzz[:, :, :nq], dzz[:, :, nq:2 * nq], dzz[:, :, 2 * nq:]
+
+    obj = TrackingObjective(q=np.tile(1e-1 * np.array([0.1, 3.0, 1.0, 3.0]), (H, 1)),   # flat.jl:31-35
+                            u=np.tile(np.array([1e-3, 1.0]), (H, 1)),
+                            gamma=np.full((H, m.nc), 1e-100), b=np.full((H, m.nb), 1e-100))
+    core = Newton(m, H, gait["h"], obj, 2.0e-4, NewtonOptions(r_tol=3e-4, max_iter=5))
+    ptraj, window = ref.copy(), list(range(H + 2))
+    q0, q1 = ref.q[0].copy(), ref.q[1].copy()
+    u = core.solve(dyn, q0, q1, window, ptraj, warm_start=False)   # policy(p, traj, 1)
+    assert np.isfinite(u).all()
+    # started on the reference: the plan stays on it and the control equals the reference control
+    assert np.abs(core.traj.q - ref.q[:H + 2]).max() < 5e-3
+    assert np.abs(u - ref.u[0]).max() < 5e-2 * max(1.0, np.abs(ref.u[0]).max())
+    assert np.abs(core.res).sum() / len(core.res) < 3e-4 or core.stats["iters"] == 5
+    rot_n_stride(ptraj, get_stride(m, ref))
+    window = update_window(window, H_ref)
+    assert window[0] == 1 and np.allclose(ptraj.q[0], ref.q[1])
+    assert np.allclose(ptraj.q[H_ref + 1] - ptraj.q[1], get_stride(m, ref))
