@@ -150,7 +150,8 @@ __device__ __forceinline__ void residual(const double* __restrict__ Ls, double* 
   if (hx) sc[S::O_XY + l] = x;
   if (hy) sc[S::O_XY + NX + l] = y1;
   __syncwarp();
-  double ad = cdyn, ar = fma(ry2, y2, crst);
+  // two accumulator pairs: the fp64 FMA chains are the latency that matters here
+  double ad = cdyn, ar = fma(ry2, y2, crst), ad2 = 0.0, ar2 = 0.0;
   const double* R = Ls + D::O_RES + 2 * l;
   constexpr int NJ = NX + NY;
 #pragma unroll 2
@@ -159,8 +160,8 @@ __device__ __forceinline__ void residual(const double* __restrict__ Ls, double* 
     const double2 c0 = lds2(R + (j)*G * 2), c1 = lds2(R + (j + 1) * G * 2);
     ad = fma(c0.x, v.x, ad);
     ar = fma(c0.y, v.x, ar);
-    ad = fma(c1.x, v.y, ad);
-    ar = fma(c1.y, v.y, ar);
+    ad2 = fma(c1.x, v.y, ad2);
+    ar2 = fma(c1.y, v.y, ar2);
   }
   if constexpr (NJ & 1) {
     const double v = sc[S::O_XY + NJ - 1];
@@ -168,6 +169,8 @@ __device__ __forceinline__ void residual(const double* __restrict__ Ls, double* 
     ad = fma(c0.x, v, ad);
     ar = fma(c0.y, v, ar);
   }
+  ad += ad2;
+  ar += ar2;
   __syncwarp();
   rdyn = hx ? ad : 0.0;
   rrst = hy ? ar : 0.0;
@@ -245,13 +248,17 @@ __device__ __forceinline__ double apply_inverse(const Ctx<D>& c, double* __restr
   using S = GroupScratch<D>;
   if (hy) sc[S::O_WV + c.mystep] = w;
   __syncwarp();
-  double a0 = 0.0, a1 = 0.0;
-  static_for<0, NY / 2>([&](auto J) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  static_for<0, NY / 4>([&](auto J) {
     constexpr int j = decltype(J)::value;
-    const double2 v = lds2(sc + S::O_WV + 2 * j);
-    a0 = fma(c.M[2 * j], v.x, a0);
-    a1 = fma(c.M[2 * j + 1], v.y, a1);
+    const double2 v = lds2(sc + S::O_WV + 4 * j), w = lds2(sc + S::O_WV + 4 * j + 2);
+    a0 = fma(c.M[4 * j], v.x, a0);
+    a1 = fma(c.M[4 * j + 1], v.y, a1);
+    a2 = fma(c.M[4 * j + 2], w.x, a2);
+    a3 = fma(c.M[4 * j + 3], w.y, a3);
   });
+  a0 = (a0 + a1) + (a2 + a3);
+  a1 = 0.0;
   if (hy) sc[S::O_TV + c.mystep] = a0 + a1;
   __syncwarp();
   return hy ? sc[S::O_TV + l] : 0.0;

@@ -61,15 +61,16 @@ struct NewtonSmem {
   static_assert(D::MODE == 0, "device Newton: :configuration mode");
   static_assert(ND <= 32, "one lane per block row");
   static constexpr int BS = ND * ND;  // one ND×ND block, column-major
-  // per-warp shared memory (doubles): candidate q, u, ν; rhs/solution; d; r_x; six sliding-window blocks
+  // per-warp shared memory (doubles): candidate q, u, ν; rhs/solution; d; r_x; Q⁻¹; six sliding-window
+  // factor blocks; a three-stage window of δz blocks
   __host__ __device__ static constexpr int per_warp(int H) {
-    return (H + 2) * NQ + H * NU + 3 * H * ND + H * (NU + NQ) + 6 * BS + 8;
+    return (H + 2) * NQ + H * NU + 3 * H * ND + 2 * H * (NU + NQ) + 6 * BS + 3 * ND * NCOL + 8;
   }
   // global scratch per rollout: the three block columns L_tt, L_{t+1,t}, L_{t+2,t} of every stage
   __host__ __device__ static constexpr size_t l_doubles(int H) { return (size_t)H * 3 * BS; }
 };
 
-constexpr int NEWTON_WARPS = 4;  // rollouts per CTA (one warp each)
+constexpr int NEWTON_WARPS = 2;  // rollouts per CTA (one warp each; 21 KB of shared memory per rollout)
 
 // One warp per rollout; everything is warp-synchronous (no __syncthreads).
 //
@@ -97,7 +98,9 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
   double* gv = cnu + H * ND;            // H×ND   rhs → y → Δν
   double* dv = gv + H * ND;             // H×ND   d_t
   double* rx = dv + H * ND;             // H×NR   [r_u; r_q] per stage
-  double* blk = rx + H * NR;            // 6 blocks
+  double* qi = rx + H * NR;             // H×NR   Q⁻¹ (diagonal)
+  double* blk = qi + H * NR;            // 6 factor blocks
+  double* zwin = blk + 6 * BS;          // δz of stages t, t+1, t+2 (ring of 3)
 
   const double* cand_q = p.cand_q + (size_t)r * (H + 2) * NQ;
   const double* cand_u = p.cand_u + (size_t)r * H * NU;
@@ -108,8 +111,13 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
   __syncwarp();
   // δz of stage t: element (row a, column c) — the δq0 | δq1 | δu1 views (implicit_dynamics.jl:82-86)
   auto DZ = [&](int t, int c, int a) -> double { return p.dz[(((size_t)t * R + r) * NCOL + c) * ND + a]; };
-  auto QIu = [&](int t, int k) -> double { return 1.0 / p.obj_u[t * NU + k]; };
-  auto QIq = [&](int t, int k) -> double { return 1.0 / p.obj_q[t * NQ + k]; };
+  for (int e = lane; e < H * NR; e += 32) {
+    const int t = e / NR, c = e % NR;
+    qi[e] = 1.0 / (c < NU ? p.obj_u[t * NU + c] : p.obj_q[t * NQ + c - NU]);
+  }
+  __syncwarp();
+  auto QIu = [&](int t, int k) -> double { return qi[t * NR + k]; };
+  auto QIq = [&](int t, int k) -> double { return qi[t * NR + NU + k]; };
 
   // d_t = z*_t[1:nq] − q_{t+2}   (implicit_dynamics.jl:180-182)
   for (int e = lane; e < H * ND; e += 32) {
@@ -223,36 +231,47 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
     // sliding window of blocks (column-major ND×ND): working column A0, A1, A2 and the factor blocks
     // P1 = L_{t,t−1}, P2 = L_{t+1,t−1}, Q2 = L_{t,t−2} of the two previous block columns
     double *A0 = blk, *A1 = blk + BS, *A2 = blk + 2 * BS, *P1 = blk + 3 * BS, *P2 = blk + 4 * BS, *Q2 = blk + 5 * BS;
+    // δz window: stage s lives in slot s % 3 (coalesced 330-double copies, L2 → shared)
+    auto load_stage = [&](int s_) {
+      const double* src = p.dz + ((size_t)s_ * R + r) * (ND * NCOL);
+      double* dst = zwin + (s_ % 3) * (ND * NCOL);
+      for (int e = lane; e < ND * NCOL; e += 32) dst[e] = src[e];
+    };
+    auto ZW = [&](int s_, int c, int a) -> double { return zwin[(s_ % 3) * (ND * NCOL) + c * ND + a]; };
+    load_stage(0);
+    if (H > 1) load_stage(1);
     for (int t = 0; t < H; ++t) {
+      if (t + 2 < H) load_stage(t + 2);
+      __syncwarp();
       // ---- assemble block column t of Y minus the pending Cholesky updates ----
       for (int e = lane; e < BS; e += 32) {
         const int a = e % ND, b = e / ND;
         // (t,t): δu1 Qu⁻¹ δu1ᵀ + Qq_t⁻¹ + δq1 Qq_{t−1}⁻¹ δq1ᵀ + δq0 Qq_{t−2}⁻¹ δq0ᵀ + ρI   (lower triangle)
         double acc = 0.0;
         if (a >= b) {
-          for (int k = 0; k < NU; ++k) acc = fma(DZ(t, 2 * NQ + k, a) * QIu(t, k), DZ(t, 2 * NQ + k, b), acc);
+          for (int k = 0; k < NU; ++k) acc = fma(ZW(t, 2 * NQ + k, a) * QIu(t, k), ZW(t, 2 * NQ + k, b), acc);
           if (a == b) acc += QIq(t, a) + rho;
           if (t >= 1) {
-            for (int k = 0; k < NQ; ++k) acc = fma(DZ(t, NQ + k, a) * QIq(t - 1, k), DZ(t, NQ + k, b), acc);
+            for (int k = 0; k < NQ; ++k) acc = fma(ZW(t, NQ + k, a) * QIq(t - 1, k), ZW(t, NQ + k, b), acc);
             for (int k = 0; k < ND; ++k) acc = fma(-P1[a + k * ND], P1[b + k * ND], acc);
           }
           if (t >= 2) {
-            for (int k = 0; k < NQ; ++k) acc = fma(DZ(t, k, a) * QIq(t - 2, k), DZ(t, k, b), acc);
+            for (int k = 0; k < NQ; ++k) acc = fma(ZW(t, k, a) * QIq(t - 2, k), ZW(t, k, b), acc);
             for (int k = 0; k < ND; ++k) acc = fma(-Q2[a + k * ND], Q2[b + k * ND], acc);
           }
         }
         A0[e] = acc;
         // (t+1,t): −δq1_{t+1} Qq_t⁻¹ + δq0_{t+1} Qq_{t−1}⁻¹ δq1_tᵀ  − L_{t+1,t−1} L_{t,t−1}ᵀ
         if (t + 1 < H) {
-          double c1 = -DZ(t + 1, NQ + b, a) * QIq(t, b);
+          double c1 = -ZW(t + 1, NQ + b, a) * QIq(t, b);
           if (t >= 1) {
-            for (int k = 0; k < NQ; ++k) c1 = fma(DZ(t + 1, k, a) * QIq(t - 1, k), DZ(t, NQ + k, b), c1);
+            for (int k = 0; k < NQ; ++k) c1 = fma(ZW(t + 1, k, a) * QIq(t - 1, k), ZW(t, NQ + k, b), c1);
             for (int k = 0; k < ND; ++k) c1 = fma(-P2[a + k * ND], P1[b + k * ND], c1);
           }
           A1[e] = c1;
         }
         // (t+2,t): −δq0_{t+2} Qq_t⁻¹
-        if (t + 2 < H) A2[e] = -DZ(t + 2, b, a) * QIq(t, b);
+        if (t + 2 < H) A2[e] = -ZW(t + 2, b, a) * QIq(t, b);
       }
       __syncwarp();
       // ---- potrf: A0 = L Lᵀ in place (lane = row) ----
