@@ -357,7 +357,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ip_kernel_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            # measured on an 81 920-subproblem launch; DRAM traffic is per-subproblem streaming, so scale to n
+            traffic = json.load(f).get("dram_bytes_per_subproblem") * n
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

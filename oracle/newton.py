@@ -31,11 +31,14 @@ class NewtonOptions:  # newton.jl:2-11
 
 
 @dataclass
-class TrackingObjective:  # objective.jl:3-16 — diagonal weights per stage
+class TrackingObjective:
+    """`TrackingObjective` (objective.jl:3-16) and, when `v` is given, `TrackingVelocityObjective`
+    (objective.jl:18-47) with zero `v_target` / `q_target` — diagonal weights per stage."""
     q: np.ndarray  # (H, nq)
     u: np.ndarray  # (H, nu)
     gamma: np.ndarray  # (H, nc)
     b: np.ndarray  # (H, nb)
+    v: np.ndarray | None = None  # (H, nq) velocity weights
 
 
 class NewtonLayout:
@@ -112,6 +115,11 @@ class Newton:
             if self.mode == "configurationforce":
                 r[L.pr(t, L.ig)] += self.obj.gamma[t] * (traj.gamma[t] - ref.gamma[t])
                 r[L.pr(t, L.ib)] += self.obj.b[t] * (traj.b[t] - ref.b[t])
+            if self.obj.v is not None:  # gradient!(…, ::TrackingVelocityObjective)  newton_residual.jl:221-281
+                dv = self.obj.v[t] * (traj.q[t + 2] - traj.q[t + 1])
+                r[L.pr(t, L.iq)] += dv
+                if t >= 1:
+                    r[L.pr(t - 1, L.iq)] -= dv
         for i in range(H):
             if i >= 2:
                 r[L.pr(i - 2, L.iq)] += dq0[i].T @ nu[i]
@@ -133,6 +141,12 @@ class Newton:
             if self.mode == "configurationforce":
                 R[L.pr(t, L.ig), L.pr(t, L.ig)] += self.obj.gamma[t]
                 R[L.pr(t, L.ib), L.pr(t, L.ib)] += self.obj.b[t]
+            if self.obj.v is not None:  # hessian!(…, ::TrackingVelocityObjective)  newton_jacobian.jl:221-248
+                R[L.pr(t, L.iq), L.pr(t, L.iq)] += self.obj.v[t]
+                if t >= 1:
+                    R[L.pr(t - 1, L.iq), L.pr(t - 1, L.iq)] += self.obj.v[t]
+                    R[L.pr(t - 1, L.iq), L.pr(t, L.iq)] -= self.obj.v[t]
+                    R[L.pr(t, L.iq), L.pr(t - 1, L.iq)] -= self.obj.v[t]
             R[L.pr(t, L.iz), L.du(t)] -= 1.0
             R[L.du(t), L.pr(t, L.iz)] -= 1.0
         for i in range(H):
