@@ -18,8 +18,13 @@ What the reference's own tests DO pin for this path, and what `tests/` therefore
 one-step linear algebra (`test/controller/linearized_solver.jl:55-67`, `test/solver/{qr,schur}.jl`),
 converged-solution tolerances (`test/solver/ldl.jl`), the gait reproduction band
 (`test/controller/implicit_dynamics.jl:24`) and the gait residual identity
-(`test/simulator/quadruped.jl:16-19`).  The iteration below is the *definition* the CUDA path
-is held to (same inputs ⇒ same z, δz, status, iteration count).
+(`test/simulator/quadruped.jl:16-19`).  END TO END the reconstruction IS pinned: driving the reference's
+closed-loop tests with this loop (linearized MPC subproblems AND nonlinear simulator steps) reproduces the
+reference's recorded nominal tracking errors to within a few per cent — quadruped q/u/γ/b 0.0191/0.0433/
+0.377/0.0791 vs 0.0201/0.0437/0.374/0.0789 (`test/controller/mpc_quadruped.jl:61-64`), flamingo 0.0127/0.0825/
+0.441/0.0160 vs 0.0154/0.0829/0.444/0.0169 (`test/controller/mpc_flamingo.jl:72-75`); tests/test_closed_loop.py.
+The iteration below is the *definition* the CUDA path is held to (same inputs ⇒ same z, δz, status,
+iteration count).
 """
 from __future__ import annotations
 
