@@ -3,5 +3,5 @@ dojo-sim/ContactImplicitMPC.jl).  The directory name carries a dot, so import it
 repo-root shim:  `import cimpc_b200`."""
 from .capi import LIB_PATH, SYMBOLS, CimpcError, load_library  # noqa: F401
 from .solver import (ImplicitTrajectory, InteriorPointOptions, Newton, NewtonOptions,  # noqa: F401
-                     implicit_dynamics)
+                     Simulator, implicit_dynamics, simulator_options)
 from .sharding import gather_rollout_results, shard_rollouts, sum_statistics  # noqa: F401,E402

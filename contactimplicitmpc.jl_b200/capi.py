@@ -19,6 +19,7 @@ SYMBOLS = [
     "cimpc_create", "cimpc_destroy", "cimpc_get_dims", "cimpc_upload_linearization",
     "cimpc_ip_solve_batch", "cimpc_ip_solve_batch_host", "cimpc_launch_count",
     "cimpc_newton_opts_default", "cimpc_newton_create", "cimpc_newton_solve_batch", "cimpc_newton_last_sweeps",
+    "cimpc_sim_step_batch",
 ]
 
 
@@ -93,6 +94,9 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_newton_solve_batch.restype = C.c_int
     lib.cimpc_newton_last_sweeps.argtypes = [vp]
     lib.cimpc_newton_last_sweeps.restype = i32
+    lib.cimpc_sim_step_batch.argtypes = [vp, i64, dp, dp, dp, dp, C.c_double, C.c_double, C.POINTER(IPOpts), dp, dp, dp,
+                                         dp, dp, vp]
+    lib.cimpc_sim_step_batch.restype = C.c_int
     _lib = lib
     return lib
 

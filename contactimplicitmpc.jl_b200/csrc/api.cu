@@ -225,6 +225,8 @@ struct cimpc_ctx {
     int32_t last_sweeps = 0;
     bool ready = false;
   } nw;
+  double* sim_scratch = nullptr;
+  size_t sim_scratch_doubles = 0;
 };
 
 static int cuda_fail(cimpc_ctx* c, cudaError_t e, const char* where) {
@@ -328,6 +330,7 @@ int cimpc_destroy(cimpc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->lin) cudaFree(ctx->lin);
   if (ctx->nw.arena) cudaFree(ctx->nw.arena);
+  if (ctx->sim_scratch) cudaFree(ctx->sim_scratch);
   if (ctx->nw.h_active) cudaFreeHost(ctx->nw.h_active);
   if (ctx->dev) cudaFree(ctx->dev);
   if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -628,6 +631,30 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
   newton_finish_kernel<<<(R + 127) / 128, 128, 0, s>>>(p, d.nq, d.nu, u_out, q_out, info, p.r_tol, len);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_finish_kernel launch");
+  ctx->launches++;
+  return CIMPC_OK;
+}
+
+
+int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const double* q1, const double* u, const double* w,
+                         double mu, double h, const cimpc_ip_opts* opts, double* q2, double* gamma, double* b,
+                         uint8_t* status, int32_t* iters, void* stream) {
+  if (!ctx || n < 0 || n > (1 << 30) || !opts) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (n == 0) return CIMPC_OK;
+  if (!q0 || !q1 || !u || !q2 || !gamma || !b || !status || !iters) return CIMPC_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  const size_t need = ctx->entry->sim_scratch((int)n);
+  if (ctx->sim_scratch_doubles < need) {
+    if (ctx->sim_scratch) cudaFree(ctx->sim_scratch);
+    ctx->sim_scratch = nullptr; ctx->sim_scratch_doubles = 0;
+    CK(cudaMalloc(&ctx->sim_scratch, need * sizeof(double)));
+    ctx->sim_scratch_doubles = need;
+  }
+  SimParams p;
+  p.R = (int)n; p.q0 = q0; p.q1 = q1; p.u = u; p.w = w; p.mu = mu; p.h = h; p.o = *opts;
+  p.q2_out = q2; p.gamma_out = gamma; p.b_out = b; p.status = status; p.iters = iters; p.scratch = ctx->sim_scratch;
+  cudaError_t e = ctx->entry->sim_step(p, (cudaStream_t)stream);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "sim_step_kernel launch");
   ctx->launches++;
   return CIMPC_OK;
 }

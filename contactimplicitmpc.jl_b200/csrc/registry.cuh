@@ -4,6 +4,7 @@
 
 #include "ip_kernel.cuh"
 #include "newton_kernel.cuh"
+#include "sim_kernel.cuh"
 
 namespace cimpc {
 
@@ -23,6 +24,9 @@ struct ModelEntry {
   cudaError_t (*newton_reset)(const NewtonParams& p, const double* q0, const double* q1, int warm, cudaStream_t s);
   cudaError_t (*newton_step)(const NewtonParams& p, double* lscratch, cudaStream_t s);
   size_t (*newton_scratch)(int H);  // doubles of global scratch per rollout
+  // simulator step (generated residual of this robot)
+  cudaError_t (*sim_step)(const SimParams& p, cudaStream_t s);
+  size_t (*sim_scratch)(int R);  // doubles
 };
 
 constexpr int NEWTON_THREADS = 32 * NEWTON_WARPS;
@@ -51,6 +55,29 @@ cudaError_t launch_newton_step(const NewtonParams& p, double* lscratch, cudaStre
 template <class D>
 size_t newton_scratch_doubles(int H) {
   return NewtonSmem<D>::l_doubles(H);
+}
+
+constexpr int SIM_WARPS = 4;
+
+template <class GEN>
+cudaError_t launch_sim_step(const SimParams& p, cudaStream_t s) {
+  const int tiles = (p.R + 31) / 32;
+  const int grid = (tiles + SIM_WARPS - 1) / SIM_WARPS;
+  const size_t bytes = (size_t)SimLayout<GEN>::SMEM_PER_WARP * SIM_WARPS * sizeof(double);
+  static bool configured = false;
+  if (!configured && bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sim_step_kernel<GEN, SIM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)bytes);
+    if (e != cudaSuccess) return e;
+  }
+  configured = true;
+  sim_step_kernel<GEN, SIM_WARPS><<<grid, SIM_WARPS * 32, bytes, s>>>(p);
+  return cudaGetLastError();
+}
+
+template <class GEN>
+size_t sim_scratch_doubles(int R) {
+  return (size_t)((R + 31) / 32) * SimLayout<GEN>::TILE * 32;
 }
 
 constexpr int IP_THREADS = 256;
@@ -108,11 +135,14 @@ CIMPC_FOR_EACH_MODEL(CIMPC_DECLARE_ENTRY)
   const ModelEntry* entries_##name_(int* count) {                                                 \
     using D0 = Dims<nq, nu, nw, nc, nb, 0>;                                                       \
     using D1 = Dims<nq, nu, nw, nc, nb, 1>;                                                       \
+    using GEN = gen_##name_::Gen;                                                                 \
+    static_assert(GEN::NQ == nq && GEN::NU == nu && GEN::NW == nw && GEN::NC == nc && GEN::NB == nb, "generated model"); \
     static const ModelEntry e[2] = {                                                              \
         {#name_, {nq, nu, nw, nc, nb, 0}, layout_of<D0>(), &launch_ip<D0>, &occupancy_ip<D0>,     \
-         &launch_newton_reset<D0>, &launch_newton_step<D0>, &newton_scratch_doubles<D0>},         \
+         &launch_newton_reset<D0>, &launch_newton_step<D0>, &newton_scratch_doubles<D0>,          \
+         &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>},                                       \
         {#name_, {nq, nu, nw, nc, nb, 1}, layout_of<D1>(), &launch_ip<D1>, &occupancy_ip<D1>,     \
-         nullptr, nullptr, nullptr}};                                                             \
+         nullptr, nullptr, nullptr, &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>}};           \
     *count = 2;                                                                                   \
     return e;                                                                                     \
   }
