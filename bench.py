@@ -203,6 +203,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mpc", action="store_true", help="skip the batched newton_solve! (MPC steps/s) leg")
     ap.add_argument("--mpc-rollouts", type=int, default=16384)
+    ap.add_argument("--no-closed-loop", action="store_true", help="skip the on-device Monte-Carlo closed-loop leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -340,6 +341,48 @@ def main():
                "config": "newton_solve! cold start, quadruped H_mpc=10, r_tol=3e-4, max_iter=5 (monte_carlo.jl:44-48), "
                          "q1 = reference + N(0, 0.01^2)"}
 
+    # ---- closed-loop leg: the Monte-Carlo workload itself (policy + simulator on the device) ----------
+    closed = None
+    if not args.no_mpc and not args.no_closed_loop:
+        Rc = min(args.rollouts, args.mpc_rollouts)
+        N_sample = 5
+        mc = cb.MonteCarloRollouts(im, gait["q"], gait["u"], gait["mu"], 1.0, gait["h"], H_mpc=H_MPC, N_sample=N_sample,
+                                   obj_q=oq, obj_u=ou, kappa=1.0e-4, n_rollouts=Rc,
+                                   newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5))
+        lo, hi = cb.shard_rollouts(Rc * world, world, rank)
+        qinit = cb.quadruped_initial_configurations(Rc * world, seed=100)[lo:hi]
+        q1c = torch.from_numpy(qinit).to(dev)
+        v1c = torch.from_numpy(np.tile((gait["q"][1] - gait["q"][0]) / gait["h"], (Rc, 1))).to(dev)
+        H_sim_c = 10 * N_sample  # 10 MPC steps of every rollout
+        mc.run(q1c, v1c, N_sample)  # warm-up: one MPC step + N_sample simulator steps
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        l0 = im.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res_c = mc.run(q1c, v1c, H_sim_c, record_every=N_sample)
+        e1.record()
+        torch.cuda.synchronize()
+        tc = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        okc = res_c["status"].double().mean().reshape(1)
+        if dist:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            dist.all_reduce(okc, op=dist.ReduceOp.SUM)
+            okc /= world
+            # final gather of the (down-sampled: every N_sample-th step) configurations to rank 0 over NCCL
+            qg = cb.gather_rollout_results(res_c["q"].permute(1, 0, 2).contiguous(), Rc * world)
+            gathered = None if qg is None else list(qg.shape)
+        else:
+            gathered = list(res_c["q"].permute(1, 0, 2).shape)
+        closed = {"value": Rc * world * mc.mpc_steps / (float(tc.item()) * 1e-3), "unit": "MPC steps/s (closed loop)",
+                  "rollouts_per_gpu": Rc, "sim_steps": H_sim_c, "mpc_steps_per_rollout": mc.mpc_steps,
+                  "ms_total": float(tc.item()), "sim_ok_frac": float(okc.item()),
+                  "gathered_trajectory_shape": gathered,
+                  "config": "examples/quadruped/monte_carlo.jl: initial configurations from the conf_min/conf_max box "
+                            "(Philox seed 100), policy every 5 simulator steps, nonlinear simulator step on the device; "
+                            "trajectories recorded every 5th step and gathered to rank 0"}
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -385,6 +428,8 @@ def main():
     }
     if mpc is not None:
         out["mpc_steps"] = mpc
+    if closed is not None:
+        out["closed_loop"] = closed
     if not args.no_cpu_baseline and world == 1:
         sample = min(n, 262144)
         v, cores, dt, mit, conv = cpu_baseline_run(lin, knot, theta, q2, sample)

@@ -5,3 +5,4 @@ from .capi import LIB_PATH, SYMBOLS, CimpcError, load_library  # noqa: F401
 from .solver import (ImplicitTrajectory, InteriorPointOptions, Newton, NewtonOptions,  # noqa: F401
                      Simulator, implicit_dynamics, simulator_options)
 from .sharding import gather_rollout_results, shard_rollouts, sum_statistics  # noqa: F401,E402
+from .rollout import MonteCarloRollouts, ReferenceWindow, quadruped_initial_configurations  # noqa: F401,E402
