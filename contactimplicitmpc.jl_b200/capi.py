@@ -90,11 +90,11 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_newton_opts_default.restype = None
     lib.cimpc_newton_create.argtypes = [vp, i32, i64, dp, dp, C.c_double, C.POINTER(NewtonOpts), C.POINTER(IPOpts)]
     lib.cimpc_newton_create.restype = C.c_int
-    lib.cimpc_newton_solve_batch.argtypes = [vp, dp, dp, dp, C.c_double, C.c_double, dp, dp, i32, dp, dp, dp, vp]
+    lib.cimpc_newton_solve_batch.argtypes = [vp, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp, i32, dp, dp, dp, vp]
     lib.cimpc_newton_solve_batch.restype = C.c_int
     lib.cimpc_newton_last_sweeps.argtypes = [vp]
     lib.cimpc_newton_last_sweeps.restype = i32
-    lib.cimpc_sim_step_batch.argtypes = [vp, i64, dp, dp, dp, dp, C.c_double, C.c_double, C.POINTER(IPOpts), dp, dp, dp,
+    lib.cimpc_sim_step_batch.argtypes = [vp, i64, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.POINTER(IPOpts), dp, dp, dp,
                                          dp, dp, vp]
     lib.cimpc_sim_step_batch.restype = C.c_int
     _lib = lib

@@ -590,8 +590,8 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
 }
 
 int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
-                             double mu, double h, const double* q0, const double* q1, int32_t warm_start,
-                             double* u_out, double* q_out, int32_t* info, void* stream) {
+                             double mu, double h, const double* q0, const double* q1, const uint8_t* active,
+                             int32_t warm_start, double* u_out, double* q_out, int32_t* info, void* stream) {
   if (!ctx || !window || !ref_q || !ref_u || !q0 || !q1 || !u_out) return CIMPC_ERR_INVALID_ARGUMENT;
   auto& nw = ctx->nw;
   if (!nw.ready) return CIMPC_ERR_NOT_INITIALIZED;
@@ -608,7 +608,7 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
   CK(cudaMemcpyAsync(nw.ref_u, ref_u, sizeof(double) * H * d.nu, cudaMemcpyHostToDevice, s));
   *nw.h_active = R;
   CK(cudaMemcpyAsync(p.n_active, nw.h_active, sizeof(int), cudaMemcpyHostToDevice, s));
-  cudaError_t e = ctx->entry->newton_reset(p, q0, q1, warm_start ? 1 : 0, s);
+  cudaError_t e = ctx->entry->newton_reset(p, q0, q1, warm_start ? 1 : 0, active, s);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_reset_kernel launch");
   ctx->launches++;
   // worst case: 1 + max_iter·(1 + 7) sweeps (newton.jl:202-269); stop as soon as no rollout is active
@@ -637,7 +637,8 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
 
 
 int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const double* q1, const double* u, const double* w,
-                         double mu, double h, const cimpc_ip_opts* opts, double* q2, double* gamma, double* b,
+                         const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts, double* q2, double* gamma,
+                         double* b,
                          uint8_t* status, int32_t* iters, void* stream) {
   if (!ctx || n < 0 || n > (1 << 30) || !opts) return CIMPC_ERR_INVALID_ARGUMENT;
   if (n == 0) return CIMPC_OK;
@@ -651,7 +652,7 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const doub
     ctx->sim_scratch_doubles = need;
   }
   SimParams p;
-  p.R = (int)n; p.q0 = q0; p.q1 = q1; p.u = u; p.w = w; p.mu = mu; p.h = h; p.o = *opts;
+  p.R = (int)n; p.q0 = q0; p.q1 = q1; p.u = u; p.w = w; p.active = active; p.mu = mu; p.h = h; p.o = *opts;
   p.q2_out = q2; p.gamma_out = gamma; p.b_out = b; p.status = status; p.iters = iters; p.scratch = ctx->sim_scratch;
   cudaError_t e = ctx->entry->sim_step(p, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "sim_step_kernel launch");

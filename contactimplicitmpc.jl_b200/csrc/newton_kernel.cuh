@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
 // reset!  (newton.jl:130-167): traj ← ref (cold) ; q[1], q[2] ← q0, q1 ; candidate ← traj ; first sweep inputs.
 template <class D, int THREADS>
 __global__ void __launch_bounds__(THREADS) newton_reset_kernel(const NewtonParams p, const double* __restrict__ q0,
-                                                               const double* __restrict__ q1, int warm_start) {
+                                                               const double* __restrict__ q1, int warm_start,
+                                                               const uint8_t* __restrict__ active) {
   constexpr int NQ = D::NQ, NU = D::NU, NW = D::NW, ND = D::ND, NTH = D::NTH;
   const int r = blockIdx.x, tid = threadIdx.x, H = p.H, R = p.R;
   if (r >= R) return;
@@ -456,9 +457,11 @@ __global__ void __launch_bounds__(THREADS) newton_reset_kernel(const NewtonParam
     const int t = e / NQ, k = e % NQ;
     p.q2[((size_t)t * R + r) * NQ + k] = traj_q[(t + 2) * NQ + k];
   }
-  for (int t = tid; t < H; t += THREADS) p.knot[(size_t)t * R + r] = p.window[t];
+  const bool on = (active == nullptr) || active[r] != 0;  // inactive rollouts (ended simulations) are not solved
+  for (int t = tid; t < H; t += THREADS) p.knot[(size_t)t * R + r] = on ? p.window[t] : -1;
   if (tid == 0) {
-    p.phase[r] = NP_INIT;
+    p.phase[r] = on ? NP_INIT : NP_DONE;
+    if (!on) atomicSub(p.n_active, 1);
     p.alpha[r] = 1.0;
     p.beta[r] = p.beta_init;
     p.r_norm[r] = 0.0;

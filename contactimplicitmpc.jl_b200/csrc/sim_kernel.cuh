@@ -28,6 +28,7 @@ struct SimParams {
   const double* q1;  // nq × R   q_{t+1}
   const double* u;   // nu × R
   const double* w;   // nw × R or null
+  const uint8_t* active;  // R or null: 0 = skip this rollout (outputs untouched)
   double mu, h;
   cimpc_ip_opts o;
   double* q2_out;     // nq × R   q_{t+2}
@@ -116,8 +117,8 @@ __global__ void __launch_bounds__(WARPS * 32) sim_step_kernel(const SimParams p)
   const int tile = blockIdx.x * WARPS + wid;
   const int rr = tile * 32 + lane;  // this lane's rollout
   if (tile * 32 >= p.R) return;
-  const bool valid = rr < p.R;
-  const int rc = valid ? rr : p.R - 1;
+  const bool valid = rr < p.R && (p.active == nullptr || p.active[rr] != 0);
+  const int rc = (rr < p.R) ? rr : p.R - 1;
   const cimpc_ip_opts o = p.o;
 
   extern __shared__ __align__(16) double sm[];

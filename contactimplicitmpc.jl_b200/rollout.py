@@ -82,19 +82,21 @@ class MonteCarloRollouts:
         for t in range(1, H_sim + 1):
             if cnt == N:
                 u_mpc, _, _ = self.newton.solve(self.ref.window, self.ref.q[:self.H + 2], self.ref.u[:self.H], self.mu_mpc,
-                                                self.h, q0_mpc, qb, warm_start=t > 1)
+                                                self.h, q0_mpc, qb, warm_start=t > 1, active=ok.to(torch.uint8))
                 u_sim = (u_mpc / N).contiguous()
                 self.ref.advance()
                 q0_mpc = qb
                 cnt = 0
                 self.mpc_steps += 1
             cnt += 1
-            q2, gam, b, st, _ = self.sim.step(qa, qb, u_sim, self.mu_sim, h_sim)
-            # a failed step ends that rollout (RoboDojo `simulate!` stops and returns false): freeze its state
-            newly_failed = ok & ~st.bool()
+            q2, gam, b, st, _ = self.sim.step(qa, qb, u_sim, self.mu_sim, h_sim, active=ok.to(torch.uint8))
+            # a failed step ends that rollout (RoboDojo `simulate!` stops and returns false): it is frozen and
+            # skipped by both kernels from here on
+            st = st.bool() | ~ok
+            newly_failed = ok & ~st
             if bool(newly_failed.any()):
                 failed_at[newly_failed] = t
-            ok &= st.bool()
+            ok &= st
             q2 = torch.where(ok[:, None], q2, qb)
             if t % record_every == 0:
                 k = t // record_every - 1

@@ -213,7 +213,7 @@ class Newton:
         capi.check(im_traj._ctx, im_traj.lib.cimpc_newton_create(
             im_traj._ctx, self.H, self.R, oq.ctypes.data, ou.ctypes.data, float(kappa), C.byref(co), C.byref(ci)))
 
-    def solve(self, window, ref_q, ref_u, mu, h, q0, q1, warm_start=False, want_q=False, stream=None):
+    def solve(self, window, ref_q, ref_u, mu, h, q0, q1, warm_start=False, want_q=False, stream=None, active=None):
         """window: (H+2,) 0-based knots; ref_q (H+2, nq), ref_u (H, nu) host arrays (shared by all rollouts);
         q0, q1: torch CUDA (R, nq) fp64.  Returns u (R, nu), q (R, H+2, nq) or None, info (R, 4) int32
         [Newton iterations, sweeps, converged, phase] as torch CUDA tensors."""
@@ -226,6 +226,8 @@ class Newton:
         for t_ in (q0, q1):
             assert t_.is_cuda and t_.dtype == torch.float64 and t_.is_contiguous() and t_.shape == (self.R, im.nq)
         dev = q0.device
+        if active is not None:
+            assert active.dtype == torch.uint8 and active.is_cuda and active.is_contiguous() and active.shape == (self.R,)
         u = torch.empty((self.R, im.nu), dtype=torch.float64, device=dev)
         q = torch.empty((self.R, self.H + 2, im.nq), dtype=torch.float64, device=dev) if want_q else None
         info = torch.empty((self.R, 4), dtype=torch.int32, device=dev)
@@ -233,7 +235,8 @@ class Newton:
             stream = torch.cuda.current_stream(dev).cuda_stream
         capi.check(im._ctx, im.lib.cimpc_newton_solve_batch(
             im._ctx, window.ctypes.data, ref_q.ctypes.data, ref_u.ctypes.data, float(mu), float(h), q0.data_ptr(),
-            q1.data_ptr(), int(bool(warm_start)), u.data_ptr(), q.data_ptr() if q is not None else None,
+            q1.data_ptr(), active.data_ptr() if active is not None else None, int(bool(warm_start)), u.data_ptr(),
+            q.data_ptr() if q is not None else None,
             info.data_ptr(), C.c_void_p(stream)))
         return u, q, info
 
@@ -272,7 +275,7 @@ class Simulator:
         except Exception:
             pass
 
-    def step(self, q0, q1, u, mu, h, w=None, opts: InteriorPointOptions | None = None, stream=None):
+    def step(self, q0, q1, u, mu, h, w=None, opts: InteriorPointOptions | None = None, stream=None, active=None):
         """q0, q1 (R, nq), u (R, nu), w (R, nw) or None: torch CUDA fp64, contiguous.
         Returns q2 (R, nq), gamma (R, nc), b (R, nb), status (R,) uint8, iters (R,) int32."""
         import torch
@@ -281,17 +284,18 @@ class Simulator:
         for t_, n_ in ((q0, self.nq), (q1, self.nq), (u, self.nu)):
             assert t_.is_cuda and t_.dtype == torch.float64 and t_.is_contiguous() and t_.shape == (R, n_)
         dev = q0.device
-        q2 = torch.empty((R, self.nq), dtype=torch.float64, device=dev)
-        gam = torch.empty((R, self.nc), dtype=torch.float64, device=dev)
-        b = torch.empty((R, self.nb), dtype=torch.float64, device=dev)
-        st = torch.empty(R, dtype=torch.uint8, device=dev)
-        it = torch.empty(R, dtype=torch.int32, device=dev)
+        # skipped rollouts (active == 0) keep q2 = q1, zero forces, status 0
+        q2 = q1.clone()
+        gam = torch.zeros((R, self.nc), dtype=torch.float64, device=dev)
+        b = torch.zeros((R, self.nb), dtype=torch.float64, device=dev)
+        st = torch.zeros(R, dtype=torch.uint8, device=dev)
+        it = torch.zeros(R, dtype=torch.int32, device=dev)
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
         co = o.to_c()
         capi.check(self._ctx, self.lib.cimpc_sim_step_batch(
             self._ctx, R, q0.data_ptr(), q1.data_ptr(), u.data_ptr(), w.data_ptr() if w is not None else None,
-            float(mu), float(h), C.byref(co), q2.data_ptr(), gam.data_ptr(), b.data_ptr(), st.data_ptr(),
+            active.data_ptr() if active is not None else None, float(mu), float(h), C.byref(co), q2.data_ptr(), gam.data_ptr(), b.data_ptr(), st.data_ptr(),
             it.data_ptr(), C.c_void_p(stream)))
         return q2, gam, b, st, it
 
