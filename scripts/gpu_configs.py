@@ -36,6 +36,13 @@ for robot, mode, H, n, kw in CONFIGS:
     nu_, nw_, nc_, nb_ = SIZES[robot][1:]
     nth = 2 * nq + nu_ + nw_ + 2; nd = nq if mode == "configuration" else nq + nc_ + nb_
     B = 8 * (nth + nq + nc_) + 8 * (nd + nd * (2 * nq + nu_)) + 5
+    nx, ny, mit = nq, 2 * nc_ + nb_, out[3].float().mean().item()
+    f_it = 2 * ny ** 3 + ny ** 2 + 4 * (2 * nx * ny + 1.5 * ny ** 2 + nx ** 2) + 6 * (nx ** 2 + 2 * nx * ny + ny ** 2)
+    f_d = 2 * ny ** 3 + (2 * nq + nu_) * 2 * (2 * nx * ny + 1.5 * ny ** 2 + nx ** 2)
+    flops = mit * f_it + f_d  # BASELINE.md §3 (reference algorithm's flop count)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    f64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))["dfma_tflops"]
     print(json.dumps({"robot": robot, "mode": mode, "H_mpc": H, "subproblems": n, "ms": ms, "subproblems_per_s": n / ms * 1e3,
-                      "algorithmic_bytes": B, "achieved_GBps": n * B / ms / 1e6, "group_lanes": im.group,
+                      "algorithmic_bytes": B, "achieved_GBps": n * B / ms / 1e6, "hbm_frac": n * B / ms / 1e6 / peaks["hbm_gbs"],
+                      "fp64_tflops_reference_count": n * flops / ms / 1e9, "fp64_frac": n * flops / ms / 1e9 / f64, "group_lanes": im.group,
                       "mean_iters": out[3].float().mean().item(), "converged": out[2].float().mean().item(), **kw}))
