@@ -59,21 +59,21 @@ size_t newton_scratch_doubles(int H) {
   return NewtonSmem<D>::l_doubles(H);
 }
 
-constexpr int SIM_WARPS = 4;
+// One CTA of GEN::NS warps per 32-rollout tile; SIM_MIN_CTAS caps the registers (65536 / (256 · 2) → 128; the register LU holds a 28-double row).
+constexpr int SIM_MIN_CTAS = 2;
 
 template <class GEN>
 cudaError_t launch_sim_step(const SimParams& p, cudaStream_t s) {
-  const int tiles = (p.R + 31) / 32;
-  const int grid = (tiles + SIM_WARPS - 1) / SIM_WARPS;
-  const size_t bytes = (size_t)SimLayout<GEN>::SMEM_PER_WARP * SIM_WARPS * sizeof(double);
+  const int grid = (p.R + 31) / 32;
+  const size_t bytes = SimLayout<GEN>::SMEM_DOUBLES * sizeof(double);
   static bool configured = false;
   if (!configured && bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(sim_step_kernel<GEN, SIM_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(sim_step_kernel<GEN, SIM_MIN_CTAS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
   }
   configured = true;
-  sim_step_kernel<GEN, SIM_WARPS><<<grid, SIM_WARPS * 32, bytes, s>>>(p);
+  sim_step_kernel<GEN, SIM_MIN_CTAS><<<grid, GEN::NS * 32, bytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -9,7 +9,21 @@ writes `csrc/gen/residual_<robot>.h`: common-subexpression-eliminated straight-l
     eval_r (z, θ, κ, r)      all nz residual rows
     eval_rz(z, θ, J)         the structural non-zeros of ∂r/∂z, in the order of RZ_ROW / RZ_COL
 with accessor functors for inputs/outputs, so the same text serves the thread-per-rollout CUDA kernels
-(strided global memory) and the host-side parity shim (plain arrays)."""
+(strided global memory) and the host-side parity shim (plain arrays).
+
+Both functions are emitted as NS independent *slices* (`eval_r_<s>`, `eval_rz_<s>`): the outputs are dealt
+to the slices by expression size (largest first onto the lightest slice) and every slice is CSE'd on its
+own.  A CTA of the simulator kernel runs slice s on warp s (same 32 rollouts, a different part of the
+outputs), which cuts the latency of the generated phases NS-fold and keeps each slice's temporaries inside
+the register budget (the single-function form needed > 255 registers and spilled).  `eval_r` / `eval_rz`
+call all slices in turn.
+
+Trigonometry is hoisted: every distinct sin/cos argument of the residual and its Jacobian (they are
+linear in z and θ: link angles at q2 and at the two midpoints) becomes a *trig atom*; `trig_arg(k, z, θ)`
+returns the k-th argument and the slices read sin / cos of the atoms through the accessor `tr(2k)`, `tr(2k+1)`.
+Atoms 0..NTRIG_VAR-1 depend on z, the rest only on θ (constant over an interior-point solve).  The kernels
+fill the table with ONE sincos call site in a rolled loop — inlining fp64 sin/cos at ≈ 400 call sites made
+a 73 k-instruction kernel that was bound by instruction fetch."""
 from __future__ import annotations
 
 import os
@@ -46,10 +60,45 @@ class _Printer(C99CodePrinter):
         return super()._print_Pow(e)
 
 
-def _emit(name, exprs, out_fmt, z, th, kappa, pr):
-    repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("x"), optimizations="basic")
-    sub = {s: sp.Symbol(f"Z({i})") for i, s in enumerate(z)}
-    sub.update({s: sp.Symbol(f"T({i})") for i, s in enumerate(th)})
+NS = 8  # slices per generated function = warps per simulator CTA
+
+
+def _deal(costs, ns=NS):
+    """Greedy balanced partition: largest expression first onto the lightest slice."""
+    bins = [[] for _ in range(ns)]
+    load = [0] * ns
+    for k in sorted(range(len(costs)), key=lambda k_: (-costs[k_], k_)):
+        b = min(range(ns), key=lambda b_: (load[b_], b_))
+        bins[b].append(k)
+        load[b] += costs[k]
+    return [sorted(b) for b in bins]
+
+
+def _hoist_trig(exprs, z):
+    """Replace sin(a)/cos(a) by symbols sn<k>/cs<k>; returns (new exprs, [arguments], #z-dependent)."""
+    args = set()
+    for e in exprs:
+        for a in e.atoms(sp.sin, sp.cos):
+            args.add(a.args[0])
+    zs = set(z)
+    var = sorted((a for a in args if a.free_symbols & zs), key=sp.default_sort_key)
+    const = sorted((a for a in args if not (a.free_symbols & zs)), key=sp.default_sort_key)
+    order = var + const
+    sub = {}
+    for k, a in enumerate(order):
+        sub[sp.sin(a)] = sp.Symbol(f"sn{k}", real=True)
+        sub[sp.cos(a)] = sp.Symbol(f"cs{k}", real=True)
+    out = [e.xreplace(sub) for e in exprs]
+    for e in out:
+        assert not e.atoms(sp.sin, sp.cos), "unhoisted trigonometric atom"
+    return out, order, len(var)
+
+
+def _emit(exprs, idx, out_fmt, z, th, pr, ntrig=0):
+    """Straight-line code for the outputs `idx` of `exprs` (own CSE)."""
+    if not idx:
+        return [], 0
+    repl, red = sp.cse([exprs[k] for k in idx], symbols=sp.numbered_symbols("x"), optimizations="basic")
     lines = []
     used = set()
     for _, e in repl:
@@ -62,10 +111,16 @@ def _emit(name, exprs, out_fmt, z, th, kappa, pr):
     for i, s in enumerate(th):
         if s in used:
             lines.append(f"  const double t{i} = th({i});")
+    names = {str(s) for s in used}
+    for k in range(ntrig):
+        if f"sn{k}" in names:
+            lines.append(f"  const double sn{k} = tr({2 * k});")
+        if f"cs{k}" in names:
+            lines.append(f"  const double cs{k} = tr({2 * k + 1});")
     for s, e in repl:
         lines.append(f"  const double {s} = {pr.doprint(e)};")
-    for i, e in enumerate(red):
-        lines.append("  " + out_fmt.format(i=i, e=pr.doprint(e)))
+    for k, e in zip(idx, red):
+        lines.append("  " + out_fmt.format(i=k, e=pr.doprint(e)))
     return lines, len(repl)
 
 
@@ -76,30 +131,60 @@ def generate(robot: str) -> str:
     rvec = sp.Matrix(r)
     J = rvec.jacobian(sp.Matrix(z))
     nnz = [(i, j) for j in range(m.nz) for i in range(m.nz) if J[i, j] != 0]  # column-major order
-    r_lines, r_tmp = _emit("r", list(r), "r({i}, {e});", z, th, kappa, pr)
-    j_lines, j_tmp = _emit("rz", [J[i, j] for i, j in nnz], "J({i}, {e});", z, th, kappa, pr)
+    hoisted, trig_args, ntv = _hoist_trig(list(r) + [J[i, j] for i, j in nnz], z)
+    nt = len(trig_args)
+    r_exprs = hoisted[:m.nz]
+    j_exprs = hoisted[m.nz:]
+    r_bins = _deal([sp.count_ops(e) + 1 for e in r_exprs])
+    j_bins = _deal([sp.count_ops(e) + 1 for e in j_exprs])
+    r_sl = [_emit(r_exprs, b, "r({i}, {e});", z, th, pr, nt) for b in r_bins]
+    j_sl = [_emit(j_exprs, b, "J({i}, {e});", z, th, pr, nt) for b in j_bins]
     tag = ROBOTS[robot]
     out = []
     out.append(f"// GENERATED by contactimplicitmpc.jl_b200/modelgen/codegen.py — do not edit.")
     out.append(f"// Nonlinear contact residual of `{robot}` (src/simulation/simulation.jl:133-158 with")
-    out.append(f"// src/dynamics/{robot}/model.jl and src/dynamics/model.jl:18-41), CSE'd straight-line code:")
-    out.append(f"// r: {r_tmp} temporaries; rz: {len(nnz)} structural non-zeros of {m.nz}x{m.nz}, {j_tmp} temporaries.")
+    out.append(f"// src/dynamics/{robot}/model.jl and src/dynamics/model.jl:18-41), CSE'd straight-line code in")
+    out.append(f"// {NS} independent slices.  r temporaries per slice: {[t for _, t in r_sl]};")
+    out.append(f"// rz: {len(nnz)} structural non-zeros of {m.nz}x{m.nz}, temporaries per slice: {[t for _, t in j_sl]}.")
     out.append("#pragma once")
     out.append("#include <math.h>")
     out.append("#ifdef __CUDACC__\n#define CIMPC_GEN_HD __host__ __device__ __forceinline__\n#else\n#define CIMPC_GEN_HD inline\n#endif")
     out.append(f"namespace cimpc {{ namespace gen_{tag} {{")
     out.append(f"constexpr int NQ = {m.nq}, NU = {m.nu}, NW = {m.nw}, NC = {m.nc}, NB = {m.nb};")
-    out.append(f"constexpr int NZ = {m.nz}, NTH = {m.ntheta}, NNZ = {len(nnz)};")
+    out.append(f"constexpr int NZ = {m.nz}, NTH = {m.ntheta}, NNZ = {len(nnz)}, NS = {NS};")
+    out.append(f"// trig atoms: sin/cos arguments; the first NTRIG_VAR depend on z, the others only on θ")
+    out.append(f"constexpr int NTRIG = {nt}, NTRIG_VAR = {ntv};")
+    zsub = {s_: sp.Symbol(f"z({i})") for i, s_ in enumerate(z)}
+    zsub.update({s_: sp.Symbol(f"th({i})") for i, s_ in enumerate(th)})
+    out.append("template <class ZA, class TA>\nCIMPC_GEN_HD double trig_arg(int k, ZA z, TA th) {")
+    out.append("  switch (k) {")
+    for k, a in enumerate(trig_args):
+        out.append(f"    case {k}: return {pr.doprint(a.xreplace(zsub))};")
+    out.append("    default: return 0.0;\n  }\n}")
+    out.append("// fills tab[2k] = sin(arg_k), tab[2k+1] = cos(arg_k) for k0 <= k < NTRIG (host-side convenience)")
+    out.append("template <class ZA, class TA>\nCIMPC_GEN_HD void eval_trig(ZA z, TA th, double* tab, int k0 = 0) {")
+    out.append("  for (int k = k0; k < NTRIG; ++k) { const double a = trig_arg(k, z, th); tab[2 * k] = sin(a); tab[2 * k + 1] = cos(a); }")
+    out.append("}")
     out.append("// structural non-zeros of rz (0-based row / column), column-major order")
     out.append("constexpr short RZ_ROW[NNZ] = {" + ", ".join(str(i) for i, _ in nnz) + "};")
     out.append("constexpr short RZ_COL[NNZ] = {" + ", ".join(str(j) for _, j in nnz) + "};")
     out.append("// z(i), th(i): input accessors; r(i, value): output sink")
+    for s_, (lines, _) in enumerate(r_sl):
+        out.append(f"template <class ZA, class TA, class TR, class RA>\nCIMPC_GEN_HD void eval_r_{s_}(ZA z, TA th, TR tr, const double kappa, RA r) {{")
+        out += lines
+        out.append("}")
     out.append("template <class ZA, class TA, class RA>\nCIMPC_GEN_HD void eval_r(ZA z, TA th, const double kappa, RA r) {")
-    out += r_lines
+    out.append("  double tab[2 * NTRIG + 2];\n  eval_trig(z, th, tab);\n  auto tr = [&](int i) { return tab[i]; };")
+    out += [f"  eval_r_{s_}(z, th, tr, kappa, r);" for s_ in range(NS)]
     out.append("}")
     out.append("// J(k, value): k-th structural non-zero (RZ_ROW[k], RZ_COL[k])")
+    for s_, (lines, _) in enumerate(j_sl):
+        out.append(f"template <class ZA, class TA, class TR, class JA>\nCIMPC_GEN_HD void eval_rz_{s_}(ZA z, TA th, TR tr, JA J) {{")
+        out += lines
+        out.append("}")
     out.append("template <class ZA, class TA, class JA>\nCIMPC_GEN_HD void eval_rz(ZA z, TA th, JA J) {")
-    out += j_lines
+    out.append("  double tab[2 * NTRIG + 2];\n  eval_trig(z, th, tab);\n  auto tr = [&](int i) { return tab[i]; };")
+    out += [f"  eval_rz_{s_}(z, th, tr, J);" for s_ in range(NS)]
     out.append("}")
     out.append("#ifdef __CUDACC__")
     out.append("static __device__ const short RZ_ROW_D[NNZ] = {" + ", ".join(str(i) for i, _ in nnz) + "};")
@@ -108,9 +193,20 @@ def generate(robot: str) -> str:
     out.append("// traits bundle consumed by the simulator kernels (csrc/sim_kernel.cuh)")
     out.append("struct Gen {")
     out.append("  static constexpr int NQ = gen_%s::NQ, NU = gen_%s::NU, NW = gen_%s::NW, NC = gen_%s::NC, NB = gen_%s::NB;" % ((tag,) * 5))
-    out.append("  static constexpr int NZ = gen_%s::NZ, NTH = gen_%s::NTH, NNZ = gen_%s::NNZ;" % ((tag,) * 3))
+    out.append("  static constexpr int NZ = gen_%s::NZ, NTH = gen_%s::NTH, NNZ = gen_%s::NNZ, NS = gen_%s::NS;" % ((tag,) * 4))
+    out.append("  static constexpr int NTRIG = gen_%s::NTRIG, NTRIG_VAR = gen_%s::NTRIG_VAR;" % ((tag,) * 2))
+    out.append("  template <class ZA, class TA> static CIMPC_GEN_HD double trig_arg(int k, ZA z, TA th) { return gen_%s::trig_arg(k, z, th); }" % tag)
     out.append("  template <class ZA, class TA, class RA> static CIMPC_GEN_HD void r(ZA z, TA th, double kappa, RA out) { eval_r(z, th, kappa, out); }")
     out.append("  template <class ZA, class TA, class JA> static CIMPC_GEN_HD void rz(ZA z, TA th, JA out) { eval_rz(z, th, out); }")
+    out.append("  // slice s of the outputs (s warp-uniform in the kernels)")
+    out.append("  template <class ZA, class TA, class TR, class RA> static CIMPC_GEN_HD void r_slice(int s, ZA z, TA th, TR tr, double kappa, RA out) {")
+    out.append("    switch (s) {")
+    out += [f"      case {s_}: eval_r_{s_}(z, th, tr, kappa, out); break;" for s_ in range(NS)]
+    out.append("      default: break;\n    }\n  }")
+    out.append("  template <class ZA, class TA, class TR, class JA> static CIMPC_GEN_HD void rz_slice(int s, ZA z, TA th, TR tr, JA out) {")
+    out.append("    switch (s) {")
+    out += [f"      case {s_}: eval_rz_{s_}(z, th, tr, out); break;" for s_ in range(NS)]
+    out.append("      default: break;\n    }\n  }")
     out.append("#ifdef __CUDACC__")
     out.append("  static __device__ __forceinline__ int row(int k) { return RZ_ROW_D[k]; }")
     out.append("  static __device__ __forceinline__ int col(int k) { return RZ_COL_D[k]; }")
