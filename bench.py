@@ -75,55 +75,102 @@ def build_workload(rank: int, rollouts: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): an NVML polling thread
+    (≈ 2 ms period — the timed region of a default run is only tens of ms); `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows = []
+        self.rows = []  # (time, sm_mhz, max_mhz, set(reasons))
         self.index = index
         self.proc = None
+        self.nvml = None
+        self._stop = False
+        self.source = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps torch's index: resolve through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hi).bus) == int(bus):
+                        h = hi
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (pynvml, h)
+            self.source = "nvml"
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll(self):
+        nv, h = self.nvml
+        R = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+             "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+             "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+             "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.time(), sm, mx, {k for k, v in R.items() if bits & v}))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+    def _read(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if ts < t0 - 0.05 or ts > t1 + 0.05:
-                continue
+        for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                self.rows.append((time.time(), float(f[0]), float(f[1]),
+                                  {nm for nm, v in zip(names, f[3:7]) if v.lower().startswith("active")}))
             except Exception:
                 continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:  # region shorter than the sampling period: take the nearest sample
-            for ts, line in self.rows[-3:]:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[0])); mx = float(f[1])
-                except Exception:
-                    pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def stop(self, t0, t1):
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"], "samples": 0}
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        note = None
+        if not inside:  # region shorter than the sampling period: take the nearest samples
+            inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+            note = "no sample inside the timed region; nearest samples used"
+        sm = [r[1] for r in inside]
+        reasons = set().union(*[r[3] for r in inside]) if inside else set()
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": inside[0][2] if inside else None,
+               "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measured_peaks():
