@@ -19,7 +19,7 @@ SYMBOLS = [
     "cimpc_create", "cimpc_destroy", "cimpc_get_dims", "cimpc_upload_linearization",
     "cimpc_ip_solve_batch", "cimpc_ip_solve_batch_host", "cimpc_launch_count",
     "cimpc_newton_opts_default", "cimpc_newton_create", "cimpc_newton_solve_batch", "cimpc_newton_last_sweeps",
-    "cimpc_sim_step_batch",
+    "cimpc_sim_step_batch", "cimpc_linearize", "cimpc_get_linearization",
 ]
 
 
@@ -97,6 +97,10 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_sim_step_batch.argtypes = [vp, i64, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.POINTER(IPOpts), dp, dp, dp,
                                          dp, dp, vp]
     lib.cimpc_sim_step_batch.restype = C.c_int
+    lib.cimpc_linearize.argtypes = [vp, i32, dp, dp, C.c_double, vp]
+    lib.cimpc_linearize.restype = C.c_int
+    lib.cimpc_get_linearization.argtypes = [vp, dp, dp, dp]
+    lib.cimpc_get_linearization.restype = C.c_int
     _lib = lib
     return lib
 

@@ -227,6 +227,8 @@ struct cimpc_ctx {
   } nw;
   double* sim_scratch = nullptr;
   size_t sim_scratch_doubles = 0;
+  double* dense = nullptr;  // dense linearization arrays of the current reference (see alloc_dense)
+  int32_t dense_h = 0;
 };
 
 static int cuda_fail(cimpc_ctx* c, cudaError_t e, const char* where) {
@@ -331,6 +333,7 @@ int cimpc_destroy(cimpc_ctx* ctx) {
   if (ctx->lin) cudaFree(ctx->lin);
   if (ctx->nw.arena) cudaFree(ctx->nw.arena);
   if (ctx->sim_scratch) cudaFree(ctx->sim_scratch);
+  if (ctx->dense) cudaFree(ctx->dense);
   if (ctx->nw.h_active) cudaFreeHost(ctx->nw.h_active);
   if (ctx->dev) cudaFree(ctx->dev);
   if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -347,6 +350,55 @@ int cimpc_get_dims(const cimpc_ctx* ctx, cimpc_dims* d) {
   return CIMPC_OK;
 }
 
+// Dense linearization arrays of the current reference on the device: [z0 | r0 | θ0 | rz0 | rθ0].
+static cudaError_t alloc_dense(cimpc_ctx* ctx, int32_t H) {
+  const LinLayout& l = ctx->entry->lay;
+  const size_t nz = l.nz, nth = l.nth;
+  const size_t tot = (2 * nz + nth + nz * nz + nz * nth) * (size_t)H;
+  if (ctx->dense && ctx->dense_h == H) return cudaSuccess;
+  if (ctx->dense) cudaFree(ctx->dense);
+  ctx->dense = nullptr;
+  ctx->dense_h = 0;
+  cudaError_t e = cudaMalloc(&ctx->dense, tot * sizeof(double));
+  if (e == cudaSuccess) ctx->dense_h = H;
+  return e;
+}
+struct DensePtrs { double *z0, *r0, *t0, *rz, *rt; };
+static DensePtrs dense_ptrs(const cimpc_ctx* ctx) {
+  const LinLayout& l = ctx->entry->lay;
+  const size_t nz = l.nz, nth = l.nth, H = ctx->dense_h;
+  DensePtrs d;
+  d.z0 = ctx->dense; d.r0 = d.z0 + nz * H; d.t0 = d.r0 + nz * H; d.rz = d.t0 + nth * H; d.rt = d.rz + nz * nz * H;
+  return d;
+}
+
+// RLin / RZLin / RθLin / Schur constants of every knot from the dense arrays (prep_kernel).
+static cudaError_t run_prep(cimpc_ctx* ctx, int32_t H, cudaStream_t s) {
+  const LinLayout& l = ctx->entry->lay;
+  cudaError_t e = cudaSuccess;
+  if (ctx->h_ref != H || !ctx->lin) {
+    if (ctx->lin) cudaFree(ctx->lin);
+    ctx->lin = nullptr;
+    ctx->h_ref = 0;
+    e = cudaMalloc(&ctx->lin, (size_t)H * l.stride * sizeof(double));
+    if (e != cudaSuccess) return e;
+  }
+  const DensePtrs d = dense_ptrs(ctx);
+  PrepParams pp{l, d.z0, d.t0, d.r0, d.rz, d.rt, ctx->lin};
+  const size_t smem = sizeof(double) * ((size_t)4 * l.nx * l.nx + 4 * l.nx * l.ny + 2 * l.ny * l.ny + l.ny +
+                                        (size_t)(l.nx + l.ny) * l.nth + 16);
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  prep_kernel<<<H, 128, smem, s>>>(pp);
+  ctx->launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) ctx->h_ref = H;
+  return e;
+}
+
 int cimpc_upload_linearization(cimpc_ctx* ctx, int32_t H, const double* z0, const double* th0,
                                const double* r0, const double* rz0, const double* rth0, void* stream) {
   if (!ctx || H <= 0 || !z0 || !th0 || !r0 || !rz0 || !rth0) return CIMPC_ERR_INVALID_ARGUMENT;
@@ -354,38 +406,48 @@ int cimpc_upload_linearization(cimpc_ctx* ctx, int32_t H, const double* z0, cons
   cudaStream_t s = (cudaStream_t)stream;
   const LinLayout& l = ctx->entry->lay;
   const size_t nz = l.nz, nth = l.nth;
-  const size_t n_z = nz * H, n_t = nth * H, n_rz = nz * nz * H, n_rt = nz * nth * H;
-  const size_t tot = 2 * n_z + n_t + n_rz + n_rt;
-  double* tmp = nullptr;
-  CK(cudaMalloc(&tmp, tot * sizeof(double)));
-  double* d_z0 = tmp; double* d_r0 = d_z0 + n_z; double* d_t0 = d_r0 + n_z; double* d_rz = d_t0 + n_t;
-  double* d_rt = d_rz + n_rz;
-  cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_z0, z0, n_z * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_r0, r0, n_z * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t0, th0, n_t * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rz, rz0, n_rz * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_rt, rth0, n_rt * 8, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess && (ctx->h_ref != H || !ctx->lin)) {
-    if (ctx->lin) cudaFree(ctx->lin);
-    ctx->lin = nullptr;
-    ctx->h_ref = 0;
-    e = cudaMalloc(&ctx->lin, (size_t)H * l.stride * sizeof(double));
-  }
-  if (e == cudaSuccess) {
-    PrepParams pp{l, d_z0, d_t0, d_r0, d_rz, d_rt, ctx->lin};
-    const size_t smem = sizeof(double) * ((size_t)4 * l.nx * l.nx + 4 * l.nx * l.ny + 2 * l.ny * l.ny + l.ny +
-                                          (size_t)(l.nx + l.ny) * l.nth + 16);
-    if (e == cudaSuccess && smem > 48 * 1024)
-      e = cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) prep_kernel<<<H, 128, smem, s>>>(pp);
-    ctx->launches++;
-    e = cudaGetLastError();
-  }
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(tmp);
+  CK(alloc_dense(ctx, H));
+  const DensePtrs d = dense_ptrs(ctx);
+  CK(cudaMemcpyAsync(d.z0, z0, nz * H * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.r0, r0, nz * H * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.t0, th0, nth * H * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.rz, rz0, nz * nz * H * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.rt, rth0, nz * nth * H * 8, cudaMemcpyHostToDevice, s));
+  cudaError_t e = run_prep(ctx, H, s);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "cimpc_upload_linearization");
-  ctx->h_ref = H;
+  return CIMPC_OK;
+}
+
+int cimpc_linearize(cimpc_ctx* ctx, int32_t H, const double* z0, const double* th0, double kappa, void* stream) {
+  if (!ctx || H <= 0 || !z0 || !th0) return CIMPC_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const LinLayout& l = ctx->entry->lay;
+  const size_t nz = l.nz, nth = l.nth;
+  CK(alloc_dense(ctx, H));
+  const DensePtrs d = dense_ptrs(ctx);
+  CK(cudaMemcpyAsync(d.z0, z0, nz * H * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d.t0, th0, nth * H * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(d.rz, 0, (nz * nz + nz * nth) * (size_t)H * 8, s));  // rz0 and rθ0 are contiguous
+  LinEvalParams lp{H, d.z0, d.t0, kappa, d.r0, d.rz, d.rt};
+  cudaError_t e = ctx->entry->linearize(lp, s);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "linearize_kernel launch");
+  ctx->launches++;
+  e = run_prep(ctx, H, s);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "cimpc_linearize");
+  return CIMPC_OK;
+}
+
+int cimpc_get_linearization(cimpc_ctx* ctx, double* r0, double* rz0, double* rth0) {
+  if (!ctx) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (!ctx->dense || ctx->dense_h <= 0 || ctx->dense_h != ctx->h_ref) return CIMPC_ERR_NOT_INITIALIZED;
+  CK(cudaSetDevice(ctx->device));
+  const LinLayout& l = ctx->entry->lay;
+  const size_t nz = l.nz, nth = l.nth, H = ctx->dense_h;
+  const DensePtrs d = dense_ptrs(ctx);
+  if (r0) CK(cudaMemcpy(r0, d.r0, nz * H * 8, cudaMemcpyDeviceToHost));
+  if (rz0) CK(cudaMemcpy(rz0, d.rz, nz * nz * H * 8, cudaMemcpyDeviceToHost));
+  if (rth0) CK(cudaMemcpy(rth0, d.rt, nz * nth * H * 8, cudaMemcpyDeviceToHost));
   return CIMPC_OK;
 }
 
@@ -647,6 +709,7 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const doub
   const size_t need = ctx->entry->sim_scratch((int)n);
   if (ctx->sim_scratch_doubles < need) {
     if (ctx->sim_scratch) cudaFree(ctx->sim_scratch);
+  if (ctx->dense) cudaFree(ctx->dense);
     ctx->sim_scratch = nullptr; ctx->sim_scratch_doubles = 0;
     CK(cudaMalloc(&ctx->sim_scratch, need * sizeof(double)));
     ctx->sim_scratch_doubles = need;

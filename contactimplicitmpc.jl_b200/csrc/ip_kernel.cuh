@@ -121,8 +121,8 @@ struct GroupScratch {
   static constexpr int O_XY = 0;                 // [x; y1] exchange (θ in the prologue, rdyn for the products)
   static constexpr int O_WV = O_XY + XYN;        // RHS of a solve, permuted to pivot order
   static constexpr int O_TV = O_WV + NY;         // solution of a solve, natural order
-  static constexpr int O_PROW = O_TV + NY;       // pivot row of a Gauss-Jordan step
-  static constexpr int O_SENS = O_PROW + NY;     // sensitivity workspace
+  static constexpr int O_PROW = O_TV + NY;       // pivot row of a Gauss-Jordan step, double-buffered by step parity
+  static constexpr int O_SENS = O_PROW + 2 * NY; // sensitivity workspace
   static constexpr int LDP = NY + 1;             // padded leading dimension of lane-major scratch matrices
   static constexpr int O_AIBP = O_SENS;          // NX×NY   AiB with columns permuted to pivot order
   static constexpr int A_SZ = imax(NX * NY, D::MODE ? NY * LDP : 0);  // AiBp, later aliased by S⁻¹ rows
@@ -195,19 +195,33 @@ __device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l
   using S = GroupScratch<D>;
   c.mystep = UNPIV;
   c.msc = 0.0;
-  int* pl = reinterpret_cast<int*>(sc + S::O_PROW + NY);  // O_PL when recorded (see GroupScratch)
-  (void)pl;
 #pragma unroll 1
   for (int kb = 0; kb < NY; kb += 4) {
     static_for<0, 4>([&](auto U) {
       constexpr int u = decltype(U)::value;
+      double* const prow = sc + S::O_PROW + (u & 1) * NY;
       // partial pivoting on the leading 32 bits of |a| (monotone for non-negative doubles): the chosen
       // pivot is within 2^-20 of the column maximum, which is all that stability needs
       const bool unp = (c.mystep == UNPIV) && hy;
+      // every lane forms the reciprocal of ITS candidate while the pivot search is in flight; the winner
+      // publishes it in the pivot slot of the row (that slot is read for nothing else), which takes the
+      // MUFU + Newton-step latency of 1/pivot off the critical path between publish and update
+      const double myinv = __drcp_rn(c.M[u]);
       const unsigned cand = unp ? ((unsigned)__double2hiint(c.M[u]) & 0x7fffffffu) + 1u : 0u;
-      unsigned m = cand;
+      // group maximum: one REDUX per group of the warp (independent, so one REDUX latency) instead of a
+      // log2(G)-deep shuffle chain on the critical path of every elimination step
+      unsigned m;
+      if constexpr (G == 32) {
+        m = __reduce_max_sync(FULL, cand);
+      } else if constexpr (G == 16) {
+        const unsigned m0 = __reduce_max_sync(FULL, gshift == 0 ? cand : 0u);
+        const unsigned m1 = __reduce_max_sync(FULL, gshift == 0 ? 0u : cand);
+        m = gshift == 0 ? m0 : m1;
+      } else {
+        m = cand;
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o, G));
+        for (int o = G / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(FULL, m, o, G));
+      }
       unsigned bal = __ballot_sync(FULL, cand == m);
       bal = (G == 32) ? bal : ((bal >> gshift) & ((1u << (G & 31)) - 1u));
       const int p = __ffs(bal) - 1;
@@ -217,22 +231,24 @@ __device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l
         if (RECORD_PL) reinterpret_cast<int*>(sc + S::O_PL)[kb + u] = l;
         static_for<0, NY / 2>([&](auto J) {
           constexpr int j = decltype(J)::value;
-          *reinterpret_cast<double2*>(sc + S::O_PROW + 2 * j) = make_double2(c.M[2 * j], c.M[2 * j + 1]);
+          *reinterpret_cast<double2*>(prow + 2 * j) =
+              make_double2(2 * j == u ? myinv : c.M[2 * j], 2 * j + 1 == u ? myinv : c.M[2 * j + 1]);
         });
+        c.msc = myinv;
       }
       __syncwarp();
-      const double pinv = __drcp_rn(sc[S::O_PROW + u]);
-      if (is_p) c.msc = pinv;
+      const double pinv = prow[u];
       // update factor: other rows −a_iu / piv; the pivot row itself stays (its scaling is deferred)
       const double g = is_p ? 0.0 : -c.M[u] * pinv;
       static_for<0, NY / 2>([&](auto J) {
         constexpr int j = decltype(J)::value;
-        const double2 pr = lds2(sc + S::O_PROW + 2 * j);
+        const double2 pr = lds2(prow + 2 * j);
         if constexpr (2 * j != u) c.M[2 * j] = fma(g, pr.x, c.M[2 * j]);
         if constexpr (2 * j + 1 != u) c.M[2 * j + 1] = fma(g, pr.y, c.M[2 * j + 1]);
       });
       c.M[u] = is_p ? 1.0 : g;  // new pivot-column entry (unscaled 1/piv on the pivot row)
-      __syncwarp();
+      // no second __syncwarp: the next step publishes into the OTHER buffer, and a lane reaches the publish of
+      // step u + 2 only through the __syncwarp of step u + 1, i.e. after every lane has read this buffer
     });
     // rotate the row left by four column slots
     const double t0 = c.M[0], t1 = c.M[1], t2 = c.M[2], t3 = c.M[3];

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "ip_kernel.cuh"
+#include "lin_kernel.cuh"
 #include "newton_kernel.cuh"
 #include "sim_kernel.cuh"
 
@@ -28,6 +29,8 @@ struct ModelEntry {
   // simulator step (generated residual of this robot)
   cudaError_t (*sim_step)(const SimParams& p, cudaStream_t s);
   size_t (*sim_scratch)(int R);  // doubles
+  // device linearization (generated r, rz, rθ of this robot at the reference knots)
+  cudaError_t (*linearize)(const LinEvalParams& p, cudaStream_t s);
 };
 
 constexpr int NEWTON_THREADS = 32 * NEWTON_WARPS;
@@ -80,6 +83,14 @@ cudaError_t launch_sim_step(const SimParams& p, cudaStream_t s) {
 template <class GEN>
 size_t sim_scratch_doubles(int R) {
   return (size_t)((R + 31) / 32) * SimLayout<GEN>::TILE * 32;
+}
+
+template <class GEN>
+cudaError_t launch_linearize(const LinEvalParams& p, cudaStream_t s) {
+  const size_t bytes = (size_t)2 * GEN::NTRIG * 32 * sizeof(double);
+  static_assert((size_t)2 * GEN::NTRIG * 32 * sizeof(double) <= 48 * 1024, "trig table must fit default shared memory");
+  linearize_kernel<GEN><<<(p.H + 31) / 32, GEN::NS * 32, bytes, s>>>(p);
+  return cudaGetLastError();
 }
 
 constexpr int IP_THREADS = 256;
@@ -142,9 +153,10 @@ CIMPC_FOR_EACH_MODEL(CIMPC_DECLARE_ENTRY)
     static const ModelEntry e[2] = {                                                              \
         {#name_, {nq, nu, nw, nc, nb, 0}, layout_of<D0>(), &launch_ip<D0>, &occupancy_ip<D0>,     \
          &launch_newton_reset<D0>, &launch_newton_step<D0>, &newton_scratch_doubles<D0>,          \
-         &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>},                                       \
+         &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>, &launch_linearize<GEN>},               \
         {#name_, {nq, nu, nw, nc, nb, 1}, layout_of<D1>(), &launch_ip<D1>, &occupancy_ip<D1>,     \
-         nullptr, nullptr, nullptr, &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>}};           \
+         nullptr, nullptr, nullptr, &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>,             \
+         &launch_linearize<GEN>}};                                                                \
     *count = 2;                                                                                   \
     return e;                                                                                     \
   }

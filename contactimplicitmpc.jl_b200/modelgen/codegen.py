@@ -131,27 +131,33 @@ def generate(robot: str) -> str:
     rvec = sp.Matrix(r)
     J = rvec.jacobian(sp.Matrix(z))
     nnz = [(i, j) for j in range(m.nz) for i in range(m.nz) if J[i, j] != 0]  # column-major order
-    hoisted, trig_args, ntv = _hoist_trig(list(r) + [J[i, j] for i, j in nnz], z)
+    Jt = rvec.jacobian(sp.Matrix(th))
+    nnzt = [(i, j) for j in range(m.ntheta) for i in range(m.nz) if Jt[i, j] != 0]
+    hoisted, trig_args, ntv = _hoist_trig(list(r) + [J[i, j] for i, j in nnz] + [Jt[i, j] for i, j in nnzt], z)
     nt = len(trig_args)
     r_exprs = hoisted[:m.nz]
-    j_exprs = hoisted[m.nz:]
+    j_exprs = hoisted[m.nz:m.nz + len(nnz)]
+    t_exprs = hoisted[m.nz + len(nnz):]
     r_bins = _deal([sp.count_ops(e) + 1 for e in r_exprs])
     j_bins = _deal([sp.count_ops(e) + 1 for e in j_exprs])
     r_sl = [_emit(r_exprs, b, "r({i}, {e});", z, th, pr, nt) for b in r_bins]
     j_sl = [_emit(j_exprs, b, "J({i}, {e});", z, th, pr, nt) for b in j_bins]
+    t_bins = _deal([sp.count_ops(e) + 1 for e in t_exprs])
+    t_sl = [_emit(t_exprs, b, "J({i}, {e});", z, th, pr, nt) for b in t_bins]
     tag = ROBOTS[robot]
     out = []
     out.append(f"// GENERATED by contactimplicitmpc.jl_b200/modelgen/codegen.py — do not edit.")
     out.append(f"// Nonlinear contact residual of `{robot}` (src/simulation/simulation.jl:133-158 with")
     out.append(f"// src/dynamics/{robot}/model.jl and src/dynamics/model.jl:18-41), CSE'd straight-line code in")
     out.append(f"// {NS} independent slices.  r temporaries per slice: {[t for _, t in r_sl]};")
-    out.append(f"// rz: {len(nnz)} structural non-zeros of {m.nz}x{m.nz}, temporaries per slice: {[t for _, t in j_sl]}.")
+    out.append(f"// rz: {len(nnz)} structural non-zeros of {m.nz}x{m.nz}, temporaries per slice: {[t for _, t in j_sl]};")
+    out.append(f"// rθ: {len(nnzt)} structural non-zeros of {m.nz}x{m.ntheta}, temporaries per slice: {[t for _, t in t_sl]}.")
     out.append("#pragma once")
     out.append("#include <math.h>")
     out.append("#ifdef __CUDACC__\n#define CIMPC_GEN_HD __host__ __device__ __forceinline__\n#else\n#define CIMPC_GEN_HD inline\n#endif")
     out.append(f"namespace cimpc {{ namespace gen_{tag} {{")
     out.append(f"constexpr int NQ = {m.nq}, NU = {m.nu}, NW = {m.nw}, NC = {m.nc}, NB = {m.nb};")
-    out.append(f"constexpr int NZ = {m.nz}, NTH = {m.ntheta}, NNZ = {len(nnz)}, NS = {NS};")
+    out.append(f"constexpr int NZ = {m.nz}, NTH = {m.ntheta}, NNZ = {len(nnz)}, NNZT = {len(nnzt)}, NS = {NS};")
     out.append(f"// trig atoms: sin/cos arguments; the first NTRIG_VAR depend on z, the others only on θ")
     out.append(f"constexpr int NTRIG = {nt}, NTRIG_VAR = {ntv};")
     zsub = {s_: sp.Symbol(f"z({i})") for i, s_ in enumerate(z)}
@@ -168,6 +174,9 @@ def generate(robot: str) -> str:
     out.append("// structural non-zeros of rz (0-based row / column), column-major order")
     out.append("constexpr short RZ_ROW[NNZ] = {" + ", ".join(str(i) for i, _ in nnz) + "};")
     out.append("constexpr short RZ_COL[NNZ] = {" + ", ".join(str(j) for _, j in nnz) + "};")
+    out.append("// structural non-zeros of rθ (0-based row / column), column-major order")
+    out.append("constexpr short RTH_ROW[NNZT] = {" + ", ".join(str(i) for i, _ in nnzt) + "};")
+    out.append("constexpr short RTH_COL[NNZT] = {" + ", ".join(str(j) for _, j in nnzt) + "};")
     out.append("// z(i), th(i): input accessors; r(i, value): output sink")
     for s_, (lines, _) in enumerate(r_sl):
         out.append(f"template <class ZA, class TA, class TR, class RA>\nCIMPC_GEN_HD void eval_r_{s_}(ZA z, TA th, TR tr, const double kappa, RA r) {{")
@@ -186,14 +195,25 @@ def generate(robot: str) -> str:
     out.append("  double tab[2 * NTRIG + 2];\n  eval_trig(z, th, tab);\n  auto tr = [&](int i) { return tab[i]; };")
     out += [f"  eval_rz_{s_}(z, th, tr, J);" for s_ in range(NS)]
     out.append("}")
+    out.append("// J(k, value): k-th structural non-zero of rθ (RTH_ROW[k], RTH_COL[k])")
+    for s_, (lines, _) in enumerate(t_sl):
+        out.append(f"template <class ZA, class TA, class TR, class JA>\nCIMPC_GEN_HD void eval_rth_{s_}(ZA z, TA th, TR tr, JA J) {{")
+        out += lines
+        out.append("}")
+    out.append("template <class ZA, class TA, class JA>\nCIMPC_GEN_HD void eval_rth(ZA z, TA th, JA J) {")
+    out.append("  double tab[2 * NTRIG + 2];\n  eval_trig(z, th, tab);\n  auto tr = [&](int i) { return tab[i]; };")
+    out += [f"  eval_rth_{s_}(z, th, tr, J);" for s_ in range(NS)]
+    out.append("}")
     out.append("#ifdef __CUDACC__")
+    out.append("static __device__ const short RTH_ROW_D[NNZT] = {" + ", ".join(str(i) for i, _ in nnzt) + "};")
+    out.append("static __device__ const short RTH_COL_D[NNZT] = {" + ", ".join(str(j) for _, j in nnzt) + "};")
     out.append("static __device__ const short RZ_ROW_D[NNZ] = {" + ", ".join(str(i) for i, _ in nnz) + "};")
     out.append("static __device__ const short RZ_COL_D[NNZ] = {" + ", ".join(str(j) for _, j in nnz) + "};")
     out.append("#endif")
     out.append("// traits bundle consumed by the simulator kernels (csrc/sim_kernel.cuh)")
     out.append("struct Gen {")
     out.append("  static constexpr int NQ = gen_%s::NQ, NU = gen_%s::NU, NW = gen_%s::NW, NC = gen_%s::NC, NB = gen_%s::NB;" % ((tag,) * 5))
-    out.append("  static constexpr int NZ = gen_%s::NZ, NTH = gen_%s::NTH, NNZ = gen_%s::NNZ, NS = gen_%s::NS;" % ((tag,) * 4))
+    out.append("  static constexpr int NZ = gen_%s::NZ, NTH = gen_%s::NTH, NNZ = gen_%s::NNZ, NNZT = gen_%s::NNZT, NS = gen_%s::NS;" % ((tag,) * 5))
     out.append("  static constexpr int NTRIG = gen_%s::NTRIG, NTRIG_VAR = gen_%s::NTRIG_VAR;" % ((tag,) * 2))
     out.append("  template <class ZA, class TA> static CIMPC_GEN_HD double trig_arg(int k, ZA z, TA th) { return gen_%s::trig_arg(k, z, th); }" % tag)
     out.append("  template <class ZA, class TA, class RA> static CIMPC_GEN_HD void r(ZA z, TA th, double kappa, RA out) { eval_r(z, th, kappa, out); }")
@@ -207,7 +227,13 @@ def generate(robot: str) -> str:
     out.append("    switch (s) {")
     out += [f"      case {s_}: eval_rz_{s_}(z, th, tr, out); break;" for s_ in range(NS)]
     out.append("      default: break;\n    }\n  }")
+    out.append("  template <class ZA, class TA, class TR, class JA> static CIMPC_GEN_HD void rth_slice(int s, ZA z, TA th, TR tr, JA out) {")
+    out.append("    switch (s) {")
+    out += [f"      case {s_}: eval_rth_{s_}(z, th, tr, out); break;" for s_ in range(NS)]
+    out.append("      default: break;\n    }\n  }")
     out.append("#ifdef __CUDACC__")
+    out.append("  static __device__ __forceinline__ int trow(int k) { return RTH_ROW_D[k]; }")
+    out.append("  static __device__ __forceinline__ int tcol(int k) { return RTH_COL_D[k]; }")
     out.append("  static __device__ __forceinline__ int row(int k) { return RZ_ROW_D[k]; }")
     out.append("  static __device__ __forceinline__ int col(int k) { return RZ_COL_D[k]; }")
     out.append("#endif")

@@ -69,8 +69,8 @@ class ImplicitTrajectory:
           row-major [i, j] meaning (they are transposed to Julia layout internally).
     """
 
-    def __init__(self, nq, nu, nw, nc, nb, z0, th0, r0, rz0, rth0, *, mode="configuration",
-                 opts: InteriorPointOptions | None = None, device: int = 0):
+    def __init__(self, nq, nu, nw, nc, nb, z0, th0, r0=None, rz0=None, rth0=None, *, mode="configuration",
+                 opts: InteriorPointOptions | None = None, device: int = 0, kappa: float = 0.0):
         self.lib = capi.load_library()
         self.mode = mode
         self.opts = opts or InteriorPointOptions(diff_sol=True)
@@ -84,7 +84,10 @@ class ImplicitTrajectory:
         self.group = d.group
         self.device = device
         self.H = 0
-        self.update(z0, th0, r0, rz0, rth0)
+        if r0 is None:  # `ImplicitTrajectory(ref_traj, s; κ)`: linearize on the device from (z, θ) of the reference
+            self.linearize(z0, th0, kappa)
+        else:
+            self.update(z0, th0, r0, rz0, rth0)
 
     # -- set-up / re-linearization (`update!`, linearized_solver.jl:497-565) --
     def update(self, z0, th0, r0, rz0, rth0):
@@ -99,6 +102,22 @@ class ImplicitTrajectory:
             self._ctx, H, z0.ctypes.data, th0.ctypes.data, r0.ctypes.data, rz0.ctypes.data,
             rth0.ctypes.data, None))
         self.H = H
+
+    def linearize(self, z0, th0, kappa: float = 0.0):
+        """`LinearizedStep(s, z, θ, κ)` of every knot ON THE DEVICE (linearized_step.jl:10-29): evaluates the robot's
+        code-generated r!, rz!, rθ! at (z0[t], th0[t]) and rebuilds the per-knot constants."""
+        H = np.asarray(z0).shape[0]
+        z0 = _f64(z0, (H, self.nz))
+        th0 = _f64(th0, (H, self.ntheta))
+        capi.check(self._ctx, self.lib.cimpc_linearize(self._ctx, H, z0.ctypes.data, th0.ctypes.data, float(kappa), None))
+        self.H = H
+
+    def get_linearization(self):
+        """Dense (r0 [H, nz], rz0 [H, nz, nz], rθ0 [H, nz, nθ]) currently held by the context (numpy [t, i, j])."""
+        H = self.H
+        r0 = np.empty((H, self.nz)); rz = np.empty((H, self.nz, self.nz)); rt = np.empty((H, self.ntheta, self.nz))
+        capi.check(self._ctx, self.lib.cimpc_get_linearization(self._ctx, r0.ctypes.data, rz.ctypes.data, rt.ctypes.data))
+        return r0, np.transpose(rz, (0, 2, 1)).copy(), np.transpose(rt, (0, 2, 1)).copy()
 
     def close(self):
         if self._ctx:
@@ -263,6 +282,22 @@ class Simulator:
         capi.check(None, self.lib.cimpc_create(C.byref(self._ctx), device, C.byref(desc)))
         self.nq, self.nu, self.nw, self.nc, self.nb = nq, nu, nw, nc, nb
         self.opts = opts or simulator_options()
+
+    def linearize(self, z0, th0, kappa: float = 0.0):
+        """`LinearizedStep(s, z, θ, κ)` of every knot ON THE DEVICE (linearized_step.jl:10-29): evaluates the robot's
+        code-generated r!, rz!, rθ! at (z0[t], th0[t]) and rebuilds the per-knot constants."""
+        H = np.asarray(z0).shape[0]
+        z0 = _f64(z0, (H, self.nz))
+        th0 = _f64(th0, (H, self.ntheta))
+        capi.check(self._ctx, self.lib.cimpc_linearize(self._ctx, H, z0.ctypes.data, th0.ctypes.data, float(kappa), None))
+        self.H = H
+
+    def get_linearization(self):
+        """Dense (r0 [H, nz], rz0 [H, nz, nz], rθ0 [H, nz, nθ]) currently held by the context (numpy [t, i, j])."""
+        H = self.H
+        r0 = np.empty((H, self.nz)); rz = np.empty((H, self.nz, self.nz)); rt = np.empty((H, self.ntheta, self.nz))
+        capi.check(self._ctx, self.lib.cimpc_get_linearization(self._ctx, r0.ctypes.data, rz.ctypes.data, rt.ctypes.data))
+        return r0, np.transpose(rz, (0, 2, 1)).copy(), np.transpose(rt, (0, 2, 1)).copy()
 
     def close(self):
         if self._ctx:

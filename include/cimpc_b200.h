@@ -115,6 +115,25 @@ int cimpc_upload_linearization(cimpc_ctx* ctx, int32_t H_ref, const double* z0, 
                                const double* r0, const double* rz0, const double* rth0, void* stream);
 
 /*
+ * Linearize ON THE DEVICE — replaces `LinearizedStep(s, z, θ, κ)` for every reference knot
+ * (src/controller/linearized_step.jl:10-29, called from the `ImplicitTrajectory` constructor,
+ * src/controller/implicit_dynamics.jl:56) and `update!(lin, s, z, θ)` (linearized_step.jl:48-55;
+ * `update!(RLin/RZLin/RθLin)`, src/controller/linearized_solver.jl:497-565): the code-generated `r!`, `rz!`, `rθ!`
+ * of the robot (the product's counterpart of src/simulation/code_gen_simulation.jl:114-197) are evaluated at
+ * (z0[:, t], th0[:, t], kappa) on the GPU and fed to the same set-up kernel as cimpc_upload_linearization.
+ *   z0   nz × H_ref  HOST   `ref_traj.z[t]`       th0  nθ × H_ref  HOST   `ref_traj.θ[t]`
+ *   kappa            central-path parameter of the linearization (`ref_traj.κ[1]`; enters r0's bilinear rows only)
+ * Flat terrain (`flat_2D_lc` / `flat_3D_lc`), the environment of every BASELINE.json config.
+ */
+int cimpc_linearize(cimpc_ctx* ctx, int32_t H_ref, const double* z0, const double* th0, double kappa, void* stream);
+
+/*
+ * Read back the dense linearization held by the context (`lin[t].r`, `lin[t].rz`, `lin[t].rθ`): HOST outputs
+ * r0 nz × H_ref, rz0 nz × nz × H_ref, rth0 nz × nθ × H_ref; any pointer may be NULL.
+ */
+int cimpc_get_linearization(cimpc_ctx* ctx, double* r0, double* rz0, double* rth0);
+
+/*
  * Batched `interior_point_solve!` on the linearized residual — replaces the loop
  *     for t in window[1:end-2]: z_initialize!; ip[t].θ .= traj.θ[i]; interior_point_solve!(ip[t])
  * of `implicit_dynamics!` (src/controller/implicit_dynamics.jl:156-192) for `n` independent

@@ -1,5 +1,5 @@
 """The product's generated residual code (`csrc/gen/residual_<robot>.h`, sympy → C++/CUDA by
-`modelgen/codegen.py`) against the oracle's independent restatement: same r and rz at random points.
+`modelgen/codegen.py`) against the oracle's independent restatement: same r, rz and rθ at random points.
 (The reference's analogue: test/dynamics/quadruped.jl compares code-generated against hand-written functions.)"""
 import ctypes as C
 import os
@@ -23,6 +23,11 @@ void r_eval(const double* z, const double* th, double kappa, double* r) {
 void rz_eval(const double* z, const double* th, double* J) {
   eval_rz([&](int i) { return z[i]; }, [&](int i) { return th[i]; }, [&](int k, double v) { J[k] = v; });
 }
+int nnzt() { return NNZT; }
+void pattern_t(int* row, int* col) { for (int k = 0; k < NNZT; ++k) { row[k] = RTH_ROW[k]; col[k] = RTH_COL[k]; } }
+void rth_eval(const double* z, const double* th, double* J) {
+  eval_rth([&](int i) { return z[i]; }, [&](int i) { return th[i]; }, [&](int k, double v) { J[k] = v; });
+}
 }
 '''
 
@@ -43,6 +48,9 @@ def test_generated_residual_matches_oracle(tmp_path, robot, tag):
     nnz = lib.nnz()
     row = np.zeros(nnz, np.int32); col = np.zeros(nnz, np.int32)
     lib.pattern(row.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p))
+    nnzt = lib.nnzt()
+    trow = np.zeros(nnzt, np.int32); tcol = np.zeros(nnzt, np.int32)
+    lib.pattern_t(trow.ctypes.data_as(C.c_void_p), tcol.ctypes.data_as(C.c_void_p))
     rng = np.random.default_rng(0)
     for trial in range(5):
         z = rng.random(nz) + 0.1
@@ -60,3 +68,10 @@ def test_generated_residual_matches_oracle(tmp_path, robot, tag):
         assert np.abs(dense - Jo).max() <= 1e-9 * max(1.0, np.abs(Jo).max())
         # the pattern is exactly the structural non-zero set (bilinear diagonals included)
         assert set(zip(*np.nonzero(Jo))) <= set(zip(row, col))
+        # rθ (the third generated function of code_gen_simulation.jl:150-168)
+        Jt = np.zeros(nnzt)
+        lib.rth_eval(z.ctypes.data, th.ctypes.data, Jt.ctypes.data)
+        To = res.rth(z, th)
+        dense_t = np.zeros((nz, nth)); dense_t[trow, tcol] = Jt
+        assert np.abs(dense_t - To).max() <= 1e-9 * max(1.0, np.abs(To).max())
+        assert set(zip(*np.nonzero(To))) <= set(zip(trow, tcol))
