@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libcimpc_b200.so")
+LIB_PATH = os.environ.get("CIMPC_B200_LIB") or os.path.join(HERE, "lib", "libcimpc_b200.so")
 
 # every symbol include/cimpc_b200.h declares
 SYMBOLS = [

@@ -618,7 +618,8 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
                o_ni = take(sizeof(int) * R), o_sw = take(sizeof(int) * R), o_ph = take(sizeof(int) * R),
                o_kn = take(sizeof(int32_t) * n), o_th = take(sizeof(double) * n * nth), o_q2 = take(sizeof(double) * n * nq),
                o_z = take(sizeof(double) * n * nz), o_dz = take(sizeof(double) * n * nd * ncol), o_st = take(n),
-               o_it = take(sizeof(int32_t) * n), o_na = take(sizeof(int)), o_rq = take(sizeof(double) * (H + 2) * nq),
+               o_it = take(sizeof(int32_t) * n), o_na = take(sizeof(int)), o_ac = take(sizeof(int)),
+               o_al2 = take(sizeof(int32_t) * R), o_rq = take(sizeof(double) * (H + 2) * nq),
                o_ru = take(sizeof(double) * H * nu), o_w = take(sizeof(double) * H * (nw_ > 0 ? nw_ : 1)),
                o_win = take(sizeof(int32_t) * (H + 2)), o_oq = take(sizeof(double) * H * nq),
                o_ou = take(sizeof(double) * H * nu),
@@ -636,6 +637,7 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
   p.theta = (double*)(b + o_th); p.q2 = (double*)(b + o_q2);
   nw.z = (double*)(b + o_z); nw.dz = (double*)(b + o_dz); nw.status = (uint8_t*)(b + o_st); nw.iters = (int32_t*)(b + o_it);
   p.z = nw.z; p.dz = nw.dz; p.n_active = (int*)(b + o_na);
+  p.act_count = (int*)(b + o_ac); p.act_list = (int32_t*)(b + o_al2);
   nw.ref_q = (double*)(b + o_rq); nw.ref_u = (double*)(b + o_ru); nw.w = (double*)(b + o_w);
   nw.window = (int32_t*)(b + o_win); nw.obj_q = (double*)(b + o_oq); nw.obj_u = (double*)(b + o_ou);
   p.ref_q = nw.ref_q; p.ref_u = nw.ref_u; p.w = nw.w; p.window = nw.window; p.obj_q = nw.obj_q; p.obj_u = nw.obj_u;
@@ -670,23 +672,33 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
   CK(cudaMemcpyAsync(nw.ref_u, ref_u, sizeof(double) * H * d.nu, cudaMemcpyHostToDevice, s));
   *nw.h_active = R;
   CK(cudaMemcpyAsync(p.n_active, nw.h_active, sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(p.act_count, 0, sizeof(int), s));
   cudaError_t e = ctx->entry->newton_reset(p, q0, q1, warm_start ? 1 : 0, active, s);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_reset_kernel launch");
   ctx->launches++;
-  // worst case: 1 + max_iter·(1 + 7) sweeps (newton.jl:202-269); stop as soon as no rollout is active
+  CK(cudaMemcpyAsync(nw.h_active, p.act_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  // worst case: 1 + max_iter·(1 + 7) sweeps (newton.jl:202-269); stop as soon as no rollout asks for another one.
+  // Every sweep is COMPACTED to the rollouts that still iterate (stage-major over `act_list`): late sweeps, where a
+  // few scattered rollouts are left back-tracking, cost what their subproblems cost instead of a scan of the batch.
   const int max_rounds = 1 + p.max_iter * 8 + 1;
   int sweeps = 0;
-  for (int round = 0; round < max_rounds; ++round) {
-    int rc = cimpc_ip_solve_batch(ctx, (int64_t)H * R, p.knot, p.theta, p.q2, nullptr, &nw.ip, nw.z, nw.dz, nw.status,
-                                  nw.iters, s);
-    if (rc != CIMPC_OK) return rc;
+  for (int round = 0; round < max_rounds && *nw.h_active > 0; ++round) {
+    const int n_act = *nw.h_active;
+    IpParams ip;
+    ip.n = (int64_t)H * n_act; ip.knot = p.knot; ip.theta = p.theta; ip.q2_init = p.q2; ip.alt = nullptr;
+    ip.lin = ctx->lin; ip.h_ref = ctx->h_ref; ip.z_out = nw.z; ip.dz_out = nw.dz; ip.status = nw.status;
+    ip.iters = nw.iters; ip.o = nw.ip; ip.act = p.act_list; ip.n_act = n_act; ip.R = R;
+    e = ctx->entry->launch(ip, ctx->sm_count, s);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "ip_solve_kernel launch");
+    ctx->launches++;
     ++sweeps;
+    CK(cudaMemsetAsync(p.act_count, 0, sizeof(int), s));
     e = ctx->entry->newton_step(p, nw.lscratch, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_step_kernel launch");
     ctx->launches++;
-    CK(cudaMemcpyAsync(nw.h_active, p.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(nw.h_active, p.act_count, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if (*nw.h_active <= 0) break;
   }
   nw.last_sweeps = sweeps;
   const int len = H * (d.nu + d.nq + ctx->entry->lay.nd);

@@ -48,6 +48,11 @@ struct IpParams {
   uint8_t* __restrict__ status;
   int32_t* __restrict__ iters;
   cimpc_ip_opts o;
+  // optional compaction (batched newton_solve!): slot s of the launch is subproblem (s / n_act) · R + act[s % n_act],
+  // i.e. stage-major over the rollouts that still iterate; null = slot s is subproblem s
+  const int32_t* __restrict__ act = nullptr;
+  int32_t n_act = 0;
+  int32_t R = 0;
 };
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -413,6 +418,15 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
   double* sc = scratch + (size_t)(tid / G) * KS::GS;
   const cimpc_ip_opts o = p.o;
 
+  // slot → subproblem (identity unless the launch is compacted).  32-bit arithmetic on purpose: a 64-bit division is
+  // an out-of-line call in SASS, and with that call present this kernel computed garbage (bisected on B200, nvcc 12.9).
+  const int32_t* const act = p.act;
+  const int n_act = p.n_act, nroll = p.R;
+  auto sub = [=](int64_t slot) -> int64_t {
+    if (act == nullptr) return slot;
+    const unsigned s = (unsigned)slot, t = s / (unsigned)n_act;  // a compacted launch has < 2^31 slots
+    return (int64_t)t * nroll + act[s - t * (unsigned)n_act];
+  };
   // this CTA's contiguous slice of the batch
   const int64_t c0 = p.n * (int64_t)blockIdx.x / gridDim.x, c1 = p.n * (int64_t)(blockIdx.x + 1) / gridDim.x;
   if (tid == 0) mbar_init(bar, 1);
@@ -430,17 +444,17 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
     }
     __syncthreads();
     for (int64_t i = cur + tid; i < c1; i += THREADS)
-      if (p.knot[i] >= 0) {
+      if (p.knot[sub(i)] >= 0) {
         atomicMin(&ctl[3], (int)(i - c0));
         break;
       }
     __syncthreads();
     const int64_t first = c0 + ctl[3];
     if (first >= c1) break;  // nothing left to do in this CTA's slice (CTA-uniform)
-    const int kraw = p.knot[first];
+    const int kraw = p.knot[sub(first)];
     const int kn = (kraw >= p.h_ref) ? 0 : kraw;  // range is validated by the host entry point
     for (int64_t i = first + 1 + tid; i < c1; i += THREADS) {
-      const int ki = p.knot[i];
+      const int ki = p.knot[sub(i)];
       if (ki >= 0 && ki != kraw) {
         atomicMin(&ctl[1], (int)(i - c0));
         break;
@@ -468,10 +482,11 @@ __global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
       base = __shfl_sync(FULL, base, 0);
       const int64_t wb = cur + base;
       if (wb >= seg_end) break;
-      const int64_t prob = wb + gi;
-      const bool valid = prob < seg_end && p.knot[prob] >= 0;
+      const int64_t slot = wb + gi;
+      const int64_t prob = slot < seg_end ? sub(slot) : 0;
+      const bool valid = slot < seg_end && p.knot[prob] >= 0;
       if (!__any_sync(FULL, valid)) continue;
-      const int64_t pi = valid ? prob : (int64_t)first;  // idle groups shadow an active subproblem
+      const int64_t pi = valid ? prob : sub(first);  // idle groups shadow an active subproblem
 
       Ctx<D> c;
       // prologue: θ-dependent constants  c = c0 + Rθ θ (+ alt on the impact rows)

@@ -53,6 +53,9 @@ struct NewtonParams {
   const double* z;   // H×R×nz
   const double* dz;  // H×R×(nd×ncol), column-major per subproblem
   int* n_active;     // [1] rollouts still iterating (decremented when a rollout finishes)
+  // compaction of the next implicit_dynamics! sweep: the rollouts that asked for one (unordered), and their number
+  int32_t* act_list;  // R
+  int* act_count;     // [1] zeroed by the host before every newton_step / newton_reset launch
 };
 
 template <class D>
@@ -412,6 +415,7 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
     const int t = e / NQ, k = e % NQ;
     p.q2[((size_t)t * R + r) * NQ + k] = cq[(t + 2) * NQ + k];
   }
+  if (lane == 0) p.act_list[atomicAdd(p.act_count, 1)] = r;  // this rollout takes part in the next sweep
 }
 
 // reset!  (newton.jl:130-167): traj ← ref (cold) ; q[1], q[2] ← q0, q1 ; candidate ← traj ; first sweep inputs.
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(THREADS) newton_reset_kernel(const NewtonParam
   if (tid == 0) {
     p.phase[r] = on ? NP_INIT : NP_DONE;
     if (!on) atomicSub(p.n_active, 1);
+    else p.act_list[atomicAdd(p.act_count, 1)] = r;
     p.alpha[r] = 1.0;
     p.beta[r] = p.beta_init;
     p.r_norm[r] = 0.0;
