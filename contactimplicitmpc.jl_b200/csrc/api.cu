@@ -221,6 +221,8 @@ struct cimpc_ctx {
     uint8_t* status = nullptr;
     int32_t* iters = nullptr;
     double* lscratch = nullptr;  // factor block columns of every rollout
+    double *ref_y = nullptr, *obj_y = nullptr, *obj_v = nullptr;
+    int variant = -1;  // −1: specialised kernel (:configuration, TrackingObjective); 0 / 1: general kernel without / with velocity cost
     int* h_active = nullptr;  // pinned
     int32_t last_sweeps = 0;
     bool ready = false;
@@ -593,27 +595,48 @@ void cimpc_newton_opts_default(cimpc_newton_opts* o) {
 
 int32_t cimpc_newton_last_sweeps(const cimpc_ctx* ctx) { return ctx ? ctx->nw.last_sweeps : 0; }
 
-int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q, const double* obj_u,
-                        double kappa, const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts) {
+int cimpc_newton_create_ex(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q, const double* obj_u,
+                           const double* obj_gamma, const double* obj_b, const double* obj_v, double kappa,
+                           const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts) {
   if (!ctx || H < 1 || H > 64 || R64 < 1 || R64 > (1 << 30) / H || !obj_q || !obj_u || !nopts || !ip_opts)
     return CIMPC_ERR_INVALID_ARGUMENT;
-  if (!ctx->entry->newton_step) return CIMPC_ERR_UNSUPPORTED_MODEL;  // :configurationforce instance
   if (!ctx->lin) return CIMPC_ERR_NOT_INITIALIZED;
+  const LinLayout& l = ctx->entry->lay;
+  const cimpc_model_desc& d = ctx->entry->desc;
+  const int R = (int)R64, nq = d.nq, nu = d.nu, nw_ = d.nw, nd = l.nd, nth = l.nth, nz = l.nz, ncol = l.ncol;
+  const int nyd = nd - nq;
+  // kernel variant
+  int variant = (d.mode == 0 && !obj_v) ? -1 : (obj_v ? 1 : 0);
+  double wmin = 1e300;
+  for (int e = 0; e < H * nq; ++e) wmin = obj_q[e] < wmin ? obj_q[e] : wmin;
+  for (int e = 0; e < H * nu; ++e) wmin = obj_u[e] < wmin ? obj_u[e] : wmin;
+  if (!(wmin > 0.0)) return CIMPC_ERR_INVALID_ARGUMENT;  // Q must be positive (dual Schur form)
+  if (obj_v)
+    for (int e = 0; e < H * nq; ++e)
+      if (!(obj_v[e] > 0.0)) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (nyd > 0) {
+    if (!obj_gamma || !obj_b) return CIMPC_ERR_INVALID_ARGUMENT;
+    // the force rows are eliminated as zero-weight rows (every example of the reference uses 1e-100): refuse weights
+    // that are not negligible against the configuration / control weights
+    for (int e = 0; e < H * d.nc; ++e)
+      if (!(obj_gamma[e] >= 0.0) || obj_gamma[e] > 1e-30 * wmin) return CIMPC_ERR_UNSUPPORTED_MODEL;
+    for (int e = 0; e < H * d.nb; ++e)
+      if (!(obj_b[e] >= 0.0) || obj_b[e] > 1e-30 * wmin) return CIMPC_ERR_UNSUPPORTED_MODEL;
+  }
   CK(cudaSetDevice(ctx->device));
   auto& nw = ctx->nw;
   if (nw.arena) { cudaFree(nw.arena); nw.arena = nullptr; }
   nw.ready = false;
-  const LinLayout& l = ctx->entry->lay;
-  const cimpc_model_desc& d = ctx->entry->desc;
-  const int R = (int)R64, nq = d.nq, nu = d.nu, nw_ = d.nw, nd = l.nd, nth = l.nth, nz = l.nz, ncol = l.ncol;
+  nw.variant = variant;
   const size_t n = (size_t)H * R;
+  const size_t lsc = variant < 0 ? ctx->entry->newton_scratch(H) : ctx->entry->newton_scratch_g[variant](H);
   // carve one arena
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   const size_t o_tq = take(sizeof(double) * R * (H + 2) * nq), o_tu = take(sizeof(double) * R * H * nu),
                o_nu = take(sizeof(double) * R * H * nd), o_cq = take(sizeof(double) * R * (H + 2) * nq),
                o_cu = take(sizeof(double) * R * H * nu), o_cnu = take(sizeof(double) * R * H * nd),
-               o_dl = take(sizeof(double) * R * H * (nu + nq + nd)), o_rn = take(sizeof(double) * R),
+               o_dl = take(sizeof(double) * R * H * (nu + nq + nd + nyd)), o_rn = take(sizeof(double) * R),
                o_al = take(sizeof(double) * R), o_be = take(sizeof(double) * R), o_ls = take(sizeof(int) * R),
                o_ni = take(sizeof(int) * R), o_sw = take(sizeof(int) * R), o_ph = take(sizeof(int) * R),
                o_kn = take(sizeof(int32_t) * n), o_th = take(sizeof(double) * n * nth), o_q2 = take(sizeof(double) * n * nq),
@@ -623,11 +646,15 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
                o_ru = take(sizeof(double) * H * nu), o_w = take(sizeof(double) * H * (nw_ > 0 ? nw_ : 1)),
                o_win = take(sizeof(int32_t) * (H + 2)), o_oq = take(sizeof(double) * H * nq),
                o_ou = take(sizeof(double) * H * nu),
-               o_lsc = take(sizeof(double) * R * ctx->entry->newton_scratch(H));
+               o_ty = take(sizeof(double) * R * H * (nyd > 0 ? nyd : 1)), o_cy = take(sizeof(double) * R * H * (nyd > 0 ? nyd : 1)),
+               o_ry = take(sizeof(double) * H * (nyd > 0 ? nyd : 1)), o_oy = take(sizeof(double) * H * (nyd > 0 ? nyd : 1)),
+               o_ov = take(sizeof(double) * H * nq),
+               o_lsc = take(sizeof(double) * R * lsc);
   CK(cudaMalloc(&nw.arena, off));
   CK(cudaMemset(nw.arena, 0, off));
   char* b = (char*)nw.arena;
   NewtonParams& p = nw.p;
+  p = NewtonParams{};
   p.R = R; p.H = H;
   p.traj_q = (double*)(b + o_tq); p.traj_u = (double*)(b + o_tu); p.nu = (double*)(b + o_nu);
   p.cand_q = (double*)(b + o_cq); p.cand_u = (double*)(b + o_cu); p.cand_nu = (double*)(b + o_cnu);
@@ -641,6 +668,17 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
   nw.ref_q = (double*)(b + o_rq); nw.ref_u = (double*)(b + o_ru); nw.w = (double*)(b + o_w);
   nw.window = (int32_t*)(b + o_win); nw.obj_q = (double*)(b + o_oq); nw.obj_u = (double*)(b + o_ou);
   p.ref_q = nw.ref_q; p.ref_u = nw.ref_u; p.w = nw.w; p.window = nw.window; p.obj_q = nw.obj_q; p.obj_u = nw.obj_u;
+  nw.ref_y = (double*)(b + o_ry); nw.obj_y = (double*)(b + o_oy); nw.obj_v = (double*)(b + o_ov);
+  if (nyd > 0) {
+    p.traj_y = (double*)(b + o_ty); p.cand_y = (double*)(b + o_cy); p.ref_y = nw.ref_y; p.obj_y = nw.obj_y;
+    // obj_y = [obj.γ; obj.b] per stage
+    CK(cudaMemcpy2D(nw.obj_y, sizeof(double) * nyd, obj_gamma, sizeof(double) * d.nc, sizeof(double) * d.nc, H, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(nw.obj_y + d.nc, sizeof(double) * nyd, obj_b, sizeof(double) * d.nb, sizeof(double) * d.nb, H, cudaMemcpyHostToDevice));
+  }
+  if (obj_v) {
+    p.obj_v = nw.obj_v;
+    CK(cudaMemcpy(nw.obj_v, obj_v, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
+  }
   nw.lscratch = (double*)(b + o_lsc);
   p.kappa = kappa; p.r_tol = nopts->r_tol; p.beta_init = nopts->beta_init; p.max_iter = nopts->max_iter;
   CK(cudaMemcpy(nw.obj_q, obj_q, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
@@ -653,12 +691,28 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* ob
   return CIMPC_OK;
 }
 
+int cimpc_newton_create(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q, const double* obj_u,
+                        double kappa, const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts) {
+  if (ctx && ctx->entry->desc.mode != 0) return CIMPC_ERR_UNSUPPORTED_MODEL;  // needs the γ, b weights: use _ex
+  return cimpc_newton_create_ex(ctx, H, R64, obj_q, obj_u, nullptr, nullptr, nullptr, kappa, nopts, ip_opts);
+}
+
 int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
                              double mu, double h, const double* q0, const double* q1, const uint8_t* active,
                              int32_t warm_start, double* u_out, double* q_out, int32_t* info, void* stream) {
+  return cimpc_newton_solve_batch_ex(ctx, window, ref_q, ref_u, nullptr, nullptr, mu, h, q0, q1, active, warm_start, u_out,
+                                     q_out, nullptr, info, stream);
+}
+
+int cimpc_newton_solve_batch_ex(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
+                                const double* ref_gamma, const double* ref_b, double mu, double h, const double* q0,
+                                const double* q1, const uint8_t* active, int32_t warm_start, double* u_out,
+                                double* q_out, double* y_out, int32_t* info, void* stream) {
   if (!ctx || !window || !ref_q || !ref_u || !q0 || !q1 || !u_out) return CIMPC_ERR_INVALID_ARGUMENT;
   auto& nw = ctx->nw;
   if (!nw.ready) return CIMPC_ERR_NOT_INITIALIZED;
+  const int nyd_ = ctx->entry->lay.nd - ctx->entry->desc.nq;
+  if (nyd_ > 0 && (!ref_gamma || !ref_b)) return CIMPC_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t s = (cudaStream_t)stream;
   NewtonParams& p = nw.p;
@@ -670,6 +724,12 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
   CK(cudaMemcpyAsync(nw.window, window, sizeof(int32_t) * (H + 2), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(nw.ref_q, ref_q, sizeof(double) * (H + 2) * d.nq, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(nw.ref_u, ref_u, sizeof(double) * H * d.nu, cudaMemcpyHostToDevice, s));
+  if (nyd_ > 0) {  // ref_y = [γ_ref; b_ref] per stage
+    CK(cudaMemcpy2DAsync(nw.ref_y, sizeof(double) * nyd_, ref_gamma, sizeof(double) * d.nc, sizeof(double) * d.nc, H,
+                         cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpy2DAsync(nw.ref_y + d.nc, sizeof(double) * nyd_, ref_b, sizeof(double) * d.nb, sizeof(double) * d.nb, H,
+                         cudaMemcpyHostToDevice, s));
+  }
   *nw.h_active = R;
   CK(cudaMemcpyAsync(p.n_active, nw.h_active, sizeof(int), cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(p.act_count, 0, sizeof(int), s));
@@ -694,15 +754,17 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
     ctx->launches++;
     ++sweeps;
     CK(cudaMemsetAsync(p.act_count, 0, sizeof(int), s));
-    e = ctx->entry->newton_step(p, nw.lscratch, s);
+    e = nw.variant < 0 ? ctx->entry->newton_step(p, nw.lscratch, s) : ctx->entry->newton_step_g[nw.variant](p, nw.lscratch, s);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_step_kernel launch");
     ctx->launches++;
     CK(cudaMemcpyAsync(nw.h_active, p.act_count, sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }
   nw.last_sweeps = sweeps;
-  const int len = H * (d.nu + d.nq + ctx->entry->lay.nd);
+  const int len = H * (d.nu + d.nq + nyd_ + ctx->entry->lay.nd);
   newton_finish_kernel<<<(R + 127) / 128, 128, 0, s>>>(p, d.nq, d.nu, u_out, q_out, info, p.r_tol, len);
+  if (y_out && nyd_ > 0)
+    CK(cudaMemcpyAsync(y_out, p.traj_y, sizeof(double) * (size_t)R * H * nyd_, cudaMemcpyDeviceToDevice, s));
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_finish_kernel launch");
   ctx->launches++;

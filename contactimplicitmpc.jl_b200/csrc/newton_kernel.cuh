@@ -56,6 +56,12 @@ struct NewtonParams {
   // compaction of the next implicit_dynamics! sweep: the rollouts that asked for one (unordered), and their number
   int32_t* act_list;  // R
   int* act_count;     // [1] zeroed by the host before every newton_step / newton_reset launch
+  // general variant only (newton_general.cuh): contact forces y = [γ; b] as Newton variables (:configurationforce)
+  // and the velocity weights of a TrackingVelocityObjective
+  double *traj_y = nullptr, *cand_y = nullptr;  // R×H×nyd
+  const double* ref_y = nullptr;                // H×nyd   `ref_traj.γ`, `ref_traj.b`
+  const double* obj_y = nullptr;                // H×nyd   diagonals of obj.γ, obj.b
+  const double* obj_v = nullptr;                // H×nq    diagonals of obj.v (null: TrackingObjective)
 };
 
 template <class D>
@@ -423,9 +429,18 @@ template <class D, int THREADS>
 __global__ void __launch_bounds__(THREADS) newton_reset_kernel(const NewtonParams p, const double* __restrict__ q0,
                                                                const double* __restrict__ q1, int warm_start,
                                                                const uint8_t* __restrict__ active) {
-  constexpr int NQ = D::NQ, NU = D::NU, NW = D::NW, ND = D::ND, NTH = D::NTH;
+  constexpr int NQ = D::NQ, NU = D::NU, NW = D::NW, ND = D::ND, NTH = D::NTH, NYD = D::NYD;
   const int r = blockIdx.x, tid = threadIdx.x, H = p.H, R = p.R;
   if (r >= R) return;
+  if constexpr (NYD > 0) {  // γ, b follow the reference on a cold start (newton.jl:139-151); candidate ← traj
+    double* ty = p.traj_y + (size_t)r * H * NYD;
+    double* cy = p.cand_y + (size_t)r * H * NYD;
+    for (int e = tid; e < H * NYD; e += THREADS) {
+      const double v = warm_start ? ty[e] : p.ref_y[e];
+      ty[e] = v;
+      cy[e] = v;
+    }
+  }
   double* traj_q = p.traj_q + (size_t)r * (H + 2) * NQ;
   double* traj_u = p.traj_u + (size_t)r * H * NU;
   double* nu = p.nu + (size_t)r * H * ND;

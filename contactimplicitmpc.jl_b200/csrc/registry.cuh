@@ -5,6 +5,7 @@
 #include "ip_kernel.cuh"
 #include "lin_kernel.cuh"
 #include "newton_kernel.cuh"
+#include "newton_general.cuh"
 #include "sim_kernel.cuh"
 
 namespace cimpc {
@@ -26,6 +27,9 @@ struct ModelEntry {
                               const uint8_t* active, cudaStream_t s);
   cudaError_t (*newton_step)(const NewtonParams& p, double* lscratch, cudaStream_t s);
   size_t (*newton_scratch)(int H);  // doubles of global scratch per rollout
+  // general device Newton (both modes; [0] TrackingObjective, [1] TrackingVelocityObjective)
+  cudaError_t (*newton_step_g[2])(const NewtonParams& p, double* lscratch, cudaStream_t s);
+  size_t (*newton_scratch_g[2])(int H);
   // simulator step (generated residual of this robot)
   cudaError_t (*sim_step)(const SimParams& p, cudaStream_t s);
   size_t (*sim_scratch)(int R);  // doubles
@@ -55,6 +59,26 @@ cudaError_t launch_newton_step(const NewtonParams& p, double* lscratch, cudaStre
   const int grid = (p.R + NEWTON_WARPS - 1) / NEWTON_WARPS;
   newton_step_kernel<D, NEWTON_THREADS><<<grid, NEWTON_THREADS, bytes, s>>>(p, lscratch);
   return cudaGetLastError();
+}
+
+template <class D, bool VEL>
+cudaError_t launch_newton_step_general(const NewtonParams& p, double* lscratch, cudaStream_t s) {
+  const size_t bytes = (size_t)NewtonGSmem<D, VEL>::per_warp(p.H) * NEWTON_WARPS * sizeof(double);
+  static size_t configured = 0;
+  if (bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(newton_step_general_kernel<D, VEL, NEWTON_THREADS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured = bytes;
+  }
+  const int grid = (p.R + NEWTON_WARPS - 1) / NEWTON_WARPS;
+  newton_step_general_kernel<D, VEL, NEWTON_THREADS><<<grid, NEWTON_THREADS, bytes, s>>>(p, lscratch);
+  return cudaGetLastError();
+}
+
+template <class D, bool VEL>
+size_t newton_scratch_general_doubles(int H) {
+  return NewtonGSmem<D, VEL>::l_doubles(H);
 }
 
 template <class D>
@@ -153,10 +177,14 @@ CIMPC_FOR_EACH_MODEL(CIMPC_DECLARE_ENTRY)
     static const ModelEntry e[2] = {                                                              \
         {#name_, {nq, nu, nw, nc, nb, 0}, layout_of<D0>(), &launch_ip<D0>, &occupancy_ip<D0>,     \
          &launch_newton_reset<D0>, &launch_newton_step<D0>, &newton_scratch_doubles<D0>,          \
+         {&launch_newton_step_general<D0, false>, &launch_newton_step_general<D0, true>},         \
+         {&newton_scratch_general_doubles<D0, false>, &newton_scratch_general_doubles<D0, true>}, \
          &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>, &launch_linearize<GEN>},               \
         {#name_, {nq, nu, nw, nc, nb, 1}, layout_of<D1>(), &launch_ip<D1>, &occupancy_ip<D1>,     \
-         nullptr, nullptr, nullptr, &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>,             \
-         &launch_linearize<GEN>}};                                                                \
+         &launch_newton_reset<D1>, nullptr, nullptr,                                              \
+         {&launch_newton_step_general<D1, false>, &launch_newton_step_general<D1, true>},         \
+         {&newton_scratch_general_doubles<D1, false>, &newton_scratch_general_doubles<D1, true>}, \
+         &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>, &launch_linearize<GEN>}};              \
     *count = 2;                                                                                   \
     return e;                                                                                     \
   }

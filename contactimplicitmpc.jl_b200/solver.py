@@ -219,29 +219,44 @@ class Newton:
     All heavy work (implicit-dynamics sweeps + KKT solves + line searches) runs on the GPU."""
 
     def __init__(self, im_traj: ImplicitTrajectory, H_mpc: int, n_rollouts: int, obj_q, obj_u, kappa: float,
-                 opts: NewtonOptions | None = None, ip_opts: InteriorPointOptions | None = None):
-        if im_traj.mode != "configuration":
-            raise ValueError("device Newton supports mode='configuration'")
+                 opts: NewtonOptions | None = None, ip_opts: InteriorPointOptions | None = None, *,
+                 obj_gamma=None, obj_b=None, obj_v=None):
+        """obj_gamma (H, nc), obj_b (H, nb): diagonals of obj.γ, obj.b — required for mode='configurationforce' (must
+        be numerically zero, as in every example of the reference); obj_v (H, nq): velocity weights of a
+        `TrackingVelocityObjective` (objective.jl:18-47) or None."""
         self.im = im_traj
         self.H, self.R = int(H_mpc), int(n_rollouts)
         self.opts = opts or NewtonOptions()
         self.ip_opts = ip_opts or im_traj.opts
+        self.force = im_traj.mode == "configurationforce"
         oq = _f64(obj_q, (self.H, im_traj.nq))
         ou = _f64(obj_u, (self.H, im_traj.nu))
+        og = _f64(obj_gamma, (self.H, im_traj.nc)) if obj_gamma is not None else None
+        ob = _f64(obj_b, (self.H, im_traj.nb)) if obj_b is not None else None
+        ov = _f64(obj_v, (self.H, im_traj.nq)) if obj_v is not None else None
+        if self.force and (og is None or ob is None):
+            raise ValueError("mode='configurationforce' needs obj_gamma and obj_b")
         co, ci = self.opts.to_c(), self.ip_opts.to_c()
-        capi.check(im_traj._ctx, im_traj.lib.cimpc_newton_create(
-            im_traj._ctx, self.H, self.R, oq.ctypes.data, ou.ctypes.data, float(kappa), C.byref(co), C.byref(ci)))
+        capi.check(im_traj._ctx, im_traj.lib.cimpc_newton_create_ex(
+            im_traj._ctx, self.H, self.R, oq.ctypes.data, ou.ctypes.data,
+            og.ctypes.data if og is not None else None, ob.ctypes.data if ob is not None else None,
+            ov.ctypes.data if ov is not None else None, float(kappa), C.byref(co), C.byref(ci)))
 
-    def solve(self, window, ref_q, ref_u, mu, h, q0, q1, warm_start=False, want_q=False, stream=None, active=None):
-        """window: (H+2,) 0-based knots; ref_q (H+2, nq), ref_u (H, nu) host arrays (shared by all rollouts);
-        q0, q1: torch CUDA (R, nq) fp64.  Returns u (R, nu), q (R, H+2, nq) or None, info (R, 4) int32
-        [Newton iterations, sweeps, converged, phase] as torch CUDA tensors."""
+    def solve(self, window, ref_q, ref_u, mu, h, q0, q1, warm_start=False, want_q=False, stream=None, active=None,
+              ref_gamma=None, ref_b=None, want_y=False):
+        """window: (H+2,) 0-based knots; ref_q (H+2, nq), ref_u (H, nu) [, ref_gamma (H, nc), ref_b (H, nb)] host arrays
+        (shared by all rollouts); q0, q1: torch CUDA (R, nq) fp64.  Returns u (R, nu), q (R, H+2, nq) or None, info (R, 4)
+        int32 [Newton iterations, sweeps, converged, phase] as torch CUDA tensors (and y (R, H, nc+nb) with want_y)."""
         import torch
         im = self.im
         window = np.ascontiguousarray(window, dtype=np.int32)
         assert window.shape == (self.H + 2,)
         ref_q = _f64(ref_q, (self.H + 2, im.nq))
         ref_u = _f64(ref_u, (self.H, im.nu))
+        rg = rb = None
+        if self.force:
+            rg = _f64(ref_gamma, (self.H, im.nc))
+            rb = _f64(ref_b, (self.H, im.nb))
         for t_ in (q0, q1):
             assert t_.is_cuda and t_.dtype == torch.float64 and t_.is_contiguous() and t_.shape == (self.R, im.nq)
         dev = q0.device
@@ -249,14 +264,19 @@ class Newton:
             assert active.dtype == torch.uint8 and active.is_cuda and active.is_contiguous() and active.shape == (self.R,)
         u = torch.empty((self.R, im.nu), dtype=torch.float64, device=dev)
         q = torch.empty((self.R, self.H + 2, im.nq), dtype=torch.float64, device=dev) if want_q else None
+        y = torch.empty((self.R, self.H, im.nc + im.nb), dtype=torch.float64, device=dev) if (want_y and self.force) else None
         info = torch.empty((self.R, 4), dtype=torch.int32, device=dev)
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
-        capi.check(im._ctx, im.lib.cimpc_newton_solve_batch(
-            im._ctx, window.ctypes.data, ref_q.ctypes.data, ref_u.ctypes.data, float(mu), float(h), q0.data_ptr(),
+        capi.check(im._ctx, im.lib.cimpc_newton_solve_batch_ex(
+            im._ctx, window.ctypes.data, ref_q.ctypes.data, ref_u.ctypes.data,
+            rg.ctypes.data if rg is not None else None, rb.ctypes.data if rb is not None else None,
+            float(mu), float(h), q0.data_ptr(),
             q1.data_ptr(), active.data_ptr() if active is not None else None, int(bool(warm_start)), u.data_ptr(),
-            q.data_ptr() if q is not None else None,
+            q.data_ptr() if q is not None else None, y.data_ptr() if y is not None else None,
             info.data_ptr(), C.c_void_p(stream)))
+        if want_y:
+            return u, q, info, y
         return u, q, info
 
     @property

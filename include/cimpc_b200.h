@@ -191,8 +191,8 @@ void cimpc_newton_opts_default(cimpc_newton_opts* opts);
  *   obj_q  nq × H_mpc   diagonals of `obj.q[t]`        obj_u  nu × H_mpc   diagonals of `obj.u[t]`
  * (`TrackingObjective`, src/controller/objective.jl:3-16; γ/b weights are unused in :configuration mode).
  * kappa = `im_traj.ip[1].κ[1]` (the dual regularisation is H·β·κ, newton_jacobian.jl:185).
- * Requires a context created with mode = 0 and an uploaded linearization.  Calling it again
- * re-allocates (e.g. for another batch size).
+ * Requires a context created with mode = 0 and an uploaded linearization (mode = 1 or a velocity objective:
+ * cimpc_newton_create_ex below).  Calling it again re-allocates (e.g. for another batch size).
  */
 int cimpc_newton_create(cimpc_ctx* ctx, int32_t H_mpc, int64_t n_rollouts, const double* obj_q,
                         const double* obj_u, double kappa, const cimpc_newton_opts* nopts,
@@ -231,6 +231,27 @@ int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double
 int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n_rollouts, const double* q0, const double* q1, const double* u,
                          const double* w, const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts,
                          double* q2, double* gamma, double* b, uint8_t* status, int32_t* iters, void* stream);
+
+/*
+ * General form of the two calls above: both modes of `ImplicitTrajectory` and both objectives.
+ *   obj_gamma nc × H_mpc, obj_b nb × H_mpc   diagonals of `obj.γ[t]`, `obj.b[t]` — required in :configurationforce mode,
+ *            where γ, b are Newton variables (newton_residual.jl:69-98); they must be numerically zero against obj_q /
+ *            obj_u (≤ 1e-30 ×; every example of the reference uses 1e-100, e.g. examples/flamingo/flat.jl:34-41):
+ *            the force rows are eliminated as zero-weight rows, otherwise CIMPC_ERR_UNSUPPORTED_MODEL
+ *   obj_v    nq × H_mpc   diagonals of `obj.v[t]` of a `TrackingVelocityObjective` (objective.jl:18-47, zero targets), all
+ *            positive, or NULL for a `TrackingObjective`
+ *   ref_gamma nc × H_mpc, ref_b nb × H_mpc  HOST: `ref_traj.γ[1:H]`, `ref_traj.b[1:H]` (cold-start values of γ, b)
+ *   y_out    (nc + nb) × H_mpc × n_rollouts DEVICE or NULL: optimised [γ; b] of every stage (`core.traj.γ`, `core.traj.b`)
+ * The Newton direction equals the reference's `R \ r` (dense / QDLDL solve of the full KKT, newton.jl:232) to round-off;
+ * it is computed through an augmented dual Schur complement (csrc/newton_general.cuh).
+ */
+int cimpc_newton_create_ex(cimpc_ctx* ctx, int32_t H_mpc, int64_t n_rollouts, const double* obj_q, const double* obj_u,
+                           const double* obj_gamma, const double* obj_b, const double* obj_v, double kappa,
+                           const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts);
+int cimpc_newton_solve_batch_ex(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
+                                const double* ref_gamma, const double* ref_b, double mu, double h, const double* q0,
+                                const double* q1, const uint8_t* active, int32_t warm_start, double* u_out,
+                                double* q_out, double* y_out, int32_t* info, void* stream);
 
 /* Sweeps (= ip_solve_kernel launches) used by the last cimpc_newton_solve_batch call. */
 int32_t cimpc_newton_last_sweeps(const cimpc_ctx* ctx);

@@ -126,3 +126,120 @@ def test_newton_warm_start_and_mpc_loop(cuda_device):
         rot_n_stride(ptraj, stride)
         window = update_window(window, H_ref)
         q0, q1 = q1, q1_next
+
+
+# ------------------------------------------------------------------------------------------------------------
+# General device Newton (newton_general.cuh): :configurationforce and / or TrackingVelocityObjective
+# ------------------------------------------------------------------------------------------------------------
+def _general_case(robot, mode, vel):
+    """Objective of test/controller/mpc_flamingo.jl:27-41 (flamingo) / monte_carlo.jl:33-37 (quadruped) with optional
+    velocity weights; returns everything both sides need."""
+    from oracle.newton import TrackingObjective
+    m, lin, gait, ref = _reference_traj(robot)
+    H = 15 if robot == "flamingo" else H_MPC
+    if robot == "flamingo":
+        oq = np.tile(1e-1 * np.array([3e2, 1e-6, 3e2, 1, 1, 1, 1, 0.1, 0.1]), (H, 1))
+        ou = np.tile(3e-1 * np.array([0.1, 0.1, 0.3, 0.3, 2, 2]), (H, 1))
+        ov = np.tile(1e-3 * np.array([1e0, 1, 1e4, 1, 1, 1, 1, 1e4, 1e4]), (H, 1))
+    else:
+        oq = np.tile(1e-2 * np.array([1.0, 0.02, 0.25] + [0.75] * (m.nq - 3)), (H, 1))
+        ou = np.tile(3e-2 * np.ones(m.nu), (H, 1))
+        ov = np.tile(1e-3 * np.array([1.0, 1.0, 1e2] + [1.0] * (m.nq - 3)), (H, 1))
+    og, ob = np.full((H, m.nc), 1e-100), np.full((H, m.nb), 1e-100)
+    obj = TrackingObjective(q=oq, u=ou, gamma=og, b=ob, v=ov if vel else None)
+    return m, lin, gait, ref, H, obj
+
+
+def _oracle_newton_general(robot, mode, m, lin, gait, H, obj, kappa, ip_kw, n_opts):
+    from oracle.c_oracle import COracle
+    from oracle.ip import IPOptions
+    from oracle.newton import Newton, NewtonOptions
+    co = COracle(*SIZES[robot], lin, mode=mode, solver="lu")
+    ipo = IPOptions(diff_sol=True, **ip_kw)
+    nq, nc, nb = m.nq, m.nc, m.nb
+    force = mode == "configurationforce"
+
+    def dyn(window, traj):
+        knot = np.array(window[:H], dtype=np.int32)
+        z, dz, st, it = co.solve(knot, traj.theta[:H], traj.q[2:H + 2], ipo)
+        nd = nq + (nc + nb if force else 0)
+        d = z[:, :nd].copy()
+        d[:, :nq] -= traj.q[2:H + 2]
+        if force:
+            d[:, nq:nq + nc] -= traj.gamma[:H]
+            d[:, nq + nc:] -= traj.b[:H]
+        return d, dz[:, :, :nq], dz[:, :, nq:2 * nq], dz[:, :, 2 * nq:]
+
+    return Newton(m, H, gait["h"], obj, kappa, NewtonOptions(**n_opts), mode=mode), dyn
+
+
+@pytest.mark.parametrize("robot,mode,vel", [("quadruped", "configuration", True),
+                                            ("flamingo", "configurationforce", False),
+                                            ("flamingo", "configurationforce", True),
+                                            ("flamingo", "configuration", True)])
+def test_general_newton_matches_oracle(cuda_device, robot, mode, vel):
+    """`newton_solve!` with γ, b as Newton variables (:configurationforce) and / or a TrackingVelocityObjective — the
+    flamingo policy of test/controller/mpc_flamingo.jl:27-56 — against the numpy oracle (dense KKT + LAPACK)."""
+    import torch
+    import cimpc_b200 as cb
+    m, lin, gait, ref, H, obj = _general_case(robot, mode, vel)
+    kappa = 2.0e-4
+    ip_kw = dict(r_tol=1e-8, kappa_tol=kappa, max_iter=100, max_ls=0, undercut=5.0)  # mpc_flamingo.jl:48-54, deterministic ls
+    n_opts = dict(r_tol=3e-4, max_iter=5)
+    R = 12
+    rng = np.random.default_rng(31)
+    q0 = np.tile(ref.q[0], (R, 1))
+    q1 = ref.q[1] + 0.005 * rng.standard_normal((R, m.nq))
+    q1[0] = ref.q[1]
+    window = np.arange(H + 2, dtype=np.int32)
+    im = cb.ImplicitTrajectory(*SIZES[robot], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"], mode=mode,
+                               opts=cb.InteriorPointOptions(diff_sol=True, **ip_kw))
+    nw = cb.Newton(im, H, R, obj.q, obj.u, kappa, cb.NewtonOptions(**n_opts), obj_gamma=obj.gamma, obj_b=obj.b, obj_v=obj.v)
+    out = nw.solve(window, ref.q[:H + 2], ref.u[:H], gait["mu"], gait["h"], torch.from_numpy(q0).to(cuda_device),
+                   torch.from_numpy(q1).to(cuda_device), want_q=True, ref_gamma=ref.gamma[:H], ref_b=ref.b[:H], want_y=True)
+    torch.cuda.synchronize()
+    u, q, info, y = (a.cpu().numpy() if a is not None else None for a in out)
+    agree, worst = 0, 0.0
+    for r in range(R):
+        core, dyn = _oracle_newton_general(robot, mode, m, lin, gait, H, obj, kappa, ip_kw, n_opts)
+        uo = core.solve(dyn, q0[r], q1[r], list(window), ref, warm_start=False)
+        if core.stats["iters"] == info[r, 0] and core.stats["ip_sweeps"] == info[r, 1]:
+            agree += 1
+            worst = max(worst, np.abs(u[r] - uo).max() / max(1.0, np.abs(uo).max()), np.abs(q[r] - core.traj.q).max())
+            if y is not None:
+                yo = np.concatenate([core.traj.gamma, core.traj.b], axis=1)
+                worst = max(worst, np.abs(y[r] - yo).max() / max(1.0, np.abs(yo).max()))
+        conv = np.abs(core.res).sum() / len(core.res) < n_opts["r_tol"]
+        assert bool(info[r, 2]) == bool(conv)
+    assert agree >= R - 1, f"only {agree}/{R} rollouts followed the oracle's iteration path"
+    # quadruped: 1e-7-level agreement; flamingo's Schur complement is ill-conditioned (cond(R) ≈ 5e5, DESIGN.md §5: two
+    # faithful CPU restatements of its IP solve differ by 2e-5), and five Newton iterations compound it (observed 3e-6)
+    assert worst <= (2e-5 if robot == "flamingo" else 1e-6), worst
+
+
+def test_general_kernel_equals_specialised_kernel(cuda_device):
+    """(:configuration, TrackingObjective) through the GENERAL kernel — selected by passing velocity weights of 1e-300,
+    which change nothing numerically — reproduces the specialised kernel: same iteration / sweep counts, u and q to
+    round-off."""
+    import torch
+    import cimpc_b200 as cb
+    m, lin, gait, ref = _reference_traj("quadruped")
+    ip_kw = dict(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, max_ls=0)
+    R = 64
+    rng = np.random.default_rng(5)
+    q0 = torch.from_numpy(np.tile(ref.q[0], (R, 1))).to(cuda_device)
+    q1 = torch.from_numpy(ref.q[1] + 0.01 * rng.standard_normal((R, m.nq))).to(cuda_device)
+    window = np.arange(H_MPC + 2, dtype=np.int32)
+    oq, ou = _objective(m)
+    res = []
+    for tiny_v in (None, np.full((H_MPC, m.nq), 1e-300)):  # a velocity weight of 1e-300 changes nothing numerically
+        im = cb.ImplicitTrajectory(*SIZES["quadruped"], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
+                                   mode="configuration", opts=cb.InteriorPointOptions(diff_sol=True, **ip_kw))
+        nw = cb.Newton(im, H_MPC, R, oq, ou, KAPPA, cb.NewtonOptions(r_tol=3e-4, max_iter=5), obj_v=tiny_v)
+        u, q, info = nw.solve(window, ref.q[:H_MPC + 2], ref.u[:H_MPC], gait["mu"], gait["h"], q0, q1, want_q=True)
+        torch.cuda.synchronize()
+        res.append((u.cpu().numpy(), q.cpu().numpy(), info.cpu().numpy()))
+    same = (res[0][2][:, :2] == res[1][2][:, :2]).all(axis=1)
+    assert same.mean() >= 0.95
+    assert np.abs(res[0][0][same] - res[1][0][same]).max() <= 1e-8
+    assert np.abs(res[0][1][same] - res[1][1][same]).max() <= 1e-8
