@@ -20,9 +20,12 @@ from .solver import ImplicitTrajectory, InteriorPointOptions, Newton, NewtonOpti
 class ReferenceWindow:
     """Host copy of the rotating reference `p.traj` (q, u) with `rot_n_stride!` and `update_window!`."""
 
-    def __init__(self, ref_q: np.ndarray, ref_u: np.ndarray, H_mpc: int):
+    def __init__(self, ref_q: np.ndarray, ref_u: np.ndarray, H_mpc: int, ref_gamma=None, ref_b=None):
         self.q0 = np.array(ref_q, dtype=np.float64)  # (H_ref+2, nq)
         self.u0 = np.array(ref_u, dtype=np.float64)  # (H_ref, nu)
+        # contact forces of the reference (Newton variables in :configurationforce mode), rotated with u
+        self.g0 = None if ref_gamma is None else np.array(ref_gamma, dtype=np.float64)
+        self.b0 = None if ref_b is None else np.array(ref_b, dtype=np.float64)
         self.H_ref, self.H = self.u0.shape[0], H_mpc
         self.stride = np.zeros(self.q0.shape[1])
         self.stride[0] = self.q0[-2, 0] - self.q0[0, 0]  # get_stride, mpc_utils.jl:103-107
@@ -30,6 +33,8 @@ class ReferenceWindow:
 
     def reset(self):  # policy.jl:100-107
         self.q, self.u = self.q0.copy(), self.u0.copy()
+        self.gamma = None if self.g0 is None else self.g0.copy()
+        self.b = None if self.b0 is None else self.b0.copy()
         self.window = np.arange(self.H + 2, dtype=np.int32)
 
     def advance(self):
@@ -38,6 +43,11 @@ class ReferenceWindow:
         self.q[:H + 1] = self.q[1:H + 2].copy()
         self.u[:H - 1] = self.u[1:H].copy()
         self.u[H - 1] = u_first
+        for a in (self.gamma, self.b):
+            if a is not None:
+                first = a[0].copy()
+                a[:H - 1] = a[1:H].copy()
+                a[H - 1] = first
         self.q[H + 1] = q_first
         for t in (H, H + 1):                                       # mpc_stride!, mpc_utils.jl:79-101
             self.q[t] = self.q[t - H] + self.stride
@@ -47,11 +57,15 @@ class ReferenceWindow:
 class MonteCarloRollouts:
     def __init__(self, im_traj: ImplicitTrajectory, ref_q, ref_u, mu_mpc, mu_sim, h, *, H_mpc, N_sample, obj_q, obj_u,
                  kappa, n_rollouts, newton_opts: NewtonOptions | None = None,
-                 sim_opts: InteriorPointOptions | None = None):
+                 sim_opts: InteriorPointOptions | None = None, obj_gamma=None, obj_b=None, obj_v=None,
+                 ref_gamma=None, ref_b=None):
+        """obj_gamma / obj_b / ref_gamma / ref_b: required when `im_traj.mode == "configurationforce"`;
+        obj_v: velocity weights of a TrackingVelocityObjective (the flamingo policy, examples/flamingo/flat.jl:34-41)."""
         self.im, self.R, self.N, self.H = im_traj, int(n_rollouts), int(N_sample), int(H_mpc)
         self.h, self.mu_mpc, self.mu_sim = float(h), float(mu_mpc), float(mu_sim)
-        self.ref = ReferenceWindow(ref_q, ref_u, H_mpc)
-        self.newton = Newton(im_traj, H_mpc, n_rollouts, obj_q, obj_u, kappa, newton_opts)
+        self.ref = ReferenceWindow(ref_q, ref_u, H_mpc, ref_gamma, ref_b)
+        self.newton = Newton(im_traj, H_mpc, n_rollouts, obj_q, obj_u, kappa, newton_opts, obj_gamma=obj_gamma,
+                             obj_b=obj_b, obj_v=obj_v)
         self.sim = Simulator(im_traj.nq, im_traj.nu, im_traj.nw, im_traj.nc, im_traj.nb, opts=sim_opts or simulator_options(),
                              device=im_traj.device)
         self.mpc_steps = 0
@@ -82,7 +96,9 @@ class MonteCarloRollouts:
         for t in range(1, H_sim + 1):
             if cnt == N:
                 u_mpc, _, _ = self.newton.solve(self.ref.window, self.ref.q[:self.H + 2], self.ref.u[:self.H], self.mu_mpc,
-                                                self.h, q0_mpc, qb, warm_start=t > 1, active=ok.to(torch.uint8))
+                                                self.h, q0_mpc, qb, warm_start=t > 1, active=ok.to(torch.uint8),
+                                                ref_gamma=None if self.ref.gamma is None else self.ref.gamma[:self.H],
+                                                ref_b=None if self.ref.b is None else self.ref.b[:self.H])
                 u_sim = (u_mpc / N).contiguous()
                 self.ref.advance()
                 q0_mpc = qb

@@ -303,22 +303,6 @@ class Simulator:
         self.nq, self.nu, self.nw, self.nc, self.nb = nq, nu, nw, nc, nb
         self.opts = opts or simulator_options()
 
-    def linearize(self, z0, th0, kappa: float = 0.0):
-        """`LinearizedStep(s, z, θ, κ)` of every knot ON THE DEVICE (linearized_step.jl:10-29): evaluates the robot's
-        code-generated r!, rz!, rθ! at (z0[t], th0[t]) and rebuilds the per-knot constants."""
-        H = np.asarray(z0).shape[0]
-        z0 = _f64(z0, (H, self.nz))
-        th0 = _f64(th0, (H, self.ntheta))
-        capi.check(self._ctx, self.lib.cimpc_linearize(self._ctx, H, z0.ctypes.data, th0.ctypes.data, float(kappa), None))
-        self.H = H
-
-    def get_linearization(self):
-        """Dense (r0 [H, nz], rz0 [H, nz, nz], rθ0 [H, nz, nθ]) currently held by the context (numpy [t, i, j])."""
-        H = self.H
-        r0 = np.empty((H, self.nz)); rz = np.empty((H, self.nz, self.nz)); rt = np.empty((H, self.ntheta, self.nz))
-        capi.check(self._ctx, self.lib.cimpc_get_linearization(self._ctx, r0.ctypes.data, rz.ctypes.data, rt.ctypes.data))
-        return r0, np.transpose(rz, (0, 2, 1)).copy(), np.transpose(rt, (0, 2, 1)).copy()
-
     def close(self):
         if self._ctx:
             self.lib.cimpc_destroy(self._ctx)

@@ -55,3 +55,48 @@ def test_monte_carlo_rollouts_on_device(cuda_device):
     e_cpu = tracking_error(ref, m, qc, uc, gc, bc, N_SAMPLE, idx_shift=(0,))
     print("CPU-oracle loop:", np.round(e_cpu, 4))
     assert np.all(np.abs(np.median(e_ok, axis=0) - e_cpu) <= 0.2 * e_cpu + 1e-3)
+
+
+def test_flamingo_closed_loop_on_device(cuda_device):
+    """test/controller/mpc_flamingo.jl:1-80 entirely on the GPU: flamingo, gait_forward_36_4, H_mpc = 15, N_sample = 5,
+    :configurationforce, TrackingVelocityObjective (general device Newton), device-side linearization, simulator with
+    γ_reg = 0 / ϵ_min = 0.05.  Reference band: q < 0.0154·1.5, u < 0.0829·1.5, γ < 0.444·1.5, b < 0.0169·1.5."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait
+    from oracle.residual import get_residual
+    from oracle.simulator import tracking_error
+    from oracle.trajectory import trajectory_from_gait
+    robot, H_mpc, N, kappa, H_sim, R = "flamingo", 15, 5, 2.0e-4, 1000, 8
+    res = get_residual(robot)
+    m = res.model
+    gait = load_gait(robot)
+    ref = trajectory_from_gait(m, gait)
+    h = gait["h"]
+    ipo = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=kappa, undercut=5.0, diff_sol=True)
+    im = cb.ImplicitTrajectory(*SIZES[robot], ref.z, ref.theta, kappa=kappa, mode="configurationforce", opts=ipo)
+    oq = np.tile(1e-1 * np.array([3e2, 1e-6, 3e2, 1, 1, 1, 1, 0.1, 0.1]), (H_mpc, 1))
+    ou = np.tile(3e-1 * np.array([0.1, 0.1, 0.3, 0.3, 2, 2]), (H_mpc, 1))
+    ov = np.tile(1e-3 * np.array([1e0, 1, 1e4, 1, 1, 1, 1, 1e4, 1e4]), (H_mpc, 1))
+    sim_opts = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=1e-8, max_ls=25, eps_min=0.05, undercut=float("inf"),
+                                       gamma_reg=0.0)
+    mc = cb.MonteCarloRollouts(im, ref.q, ref.u, ref.theta[0, -2], m.mu_world, h, H_mpc=H_mpc, N_sample=N, obj_q=oq,
+                               obj_u=ou, kappa=kappa, n_rollouts=R, newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5),
+                               sim_opts=sim_opts, obj_gamma=np.full((H_mpc, m.nc), 1e-100),
+                               obj_b=np.full((H_mpc, m.nb), 1e-100), obj_v=ov, ref_gamma=ref.gamma, ref_b=ref.b)
+    rng = np.random.default_rng(61)
+    q1 = np.tile(ref.q[1], (R, 1))
+    v1 = np.tile((ref.q[1] - ref.q[0]) / h, (R, 1))
+    v1[1:] *= 1.0 + 0.02 * rng.standard_normal((R - 1, 1))
+    out = mc.run(torch.from_numpy(q1).to(cuda_device), torch.from_numpy(v1).to(cuda_device), H_sim)
+    torch.cuda.synchronize()
+    ok = out["status"].cpu().numpy()
+    assert ok.sum() >= R // 2, f"only {ok.sum()} of {R} rollouts completed"
+    q, u, gam, b = (out[k].cpu().numpy() for k in ("q", "u", "gamma", "b"))
+    e = np.array([tracking_error(ref, m, q[:, r], u[:, r], gam[:, r], b[:, r], N, idx_shift=(0,)) for r in range(R)])
+    e_ok = e[ok]
+    print("flamingo GPU closed-loop tracking errors (q, u, γ, b):\n", np.round(e_ok, 4), "\nfailed at", out["failed_at"].cpu().numpy())
+    band = np.array([0.0154, 0.0829, 0.444, 0.0169]) * 1.5  # mpc_flamingo.jl:72-75
+    assert (np.median(e_ok, axis=0) < band).all()
+    if ok[0]:
+        assert (e[0] < band).all()  # the nominal rollout = the reference's own test
