@@ -158,15 +158,21 @@ end
 """
     newton_create!(b, H_mpc, R, obj, κ, nopts)
 
-`Newton(s, H_mpc, h, traj, im_traj; obj, opts)` (newton.jl:37-91) for R rollouts.  `obj::TrackingObjective` with
-diagonal weights (objective.jl:3-16); :configuration mode.
+`Newton(s, H_mpc, h, traj, im_traj; obj, opts)` (newton.jl:37-91) for R rollouts.  `obj`: a `TrackingObjective` or
+`TrackingVelocityObjective` with diagonal weights (objective.jl:3-47); both modes (γ, b weights numerically zero).
 """
 function newton_create!(b::B200ImplicitTrajectory, H_mpc::Int, R::Int, obj, κ::Float64, nopts::CI.NewtonOptions)
-    obj_q = reduce(hcat, (Vector(LinearAlgebra.diag(obj.q[t])) for t = 1:H_mpc))
-    obj_u = reduce(hcat, (Vector(LinearAlgebra.diag(obj.u[t])) for t = 1:H_mpc))
-    check(b.ctx, ccall((:cimpc_newton_create, LIB), Cint,
-        (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Ref{NewtonOpts}, Ref{IPOpts}),
-        b.ctx, H_mpc, R, obj_q, obj_u, κ, Ref(NewtonOpts(nopts)), Ref(b.opts)))
+    dg(f) = reduce(hcat, (Vector(LinearAlgebra.diag(getfield(obj, f)[t])) for t = 1:H_mpc))
+    obj_q, obj_u = dg(:q), dg(:u)
+    # :configurationforce needs the (numerically zero) γ, b weights; a TrackingVelocityObjective its velocity weights
+    obj_γ = b.mode == :configurationforce ? dg(:γ) : nothing
+    obj_b = b.mode == :configurationforce ? dg(:b) : nothing
+    obj_v = hasfield(typeof(obj), :v) ? dg(:v) : nothing
+    p(x) = x === nothing ? C_NULL : pointer(x)
+    GC.@preserve obj_q obj_u obj_γ obj_b obj_v check(b.ctx, ccall((:cimpc_newton_create_ex, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64,
+         Ref{NewtonOpts}, Ref{IPOpts}),
+        b.ctx, H_mpc, R, obj_q, obj_u, p(obj_γ), p(obj_b), p(obj_v), κ, Ref(NewtonOpts(nopts)), Ref(b.opts)))
 end
 
 """
@@ -180,13 +186,14 @@ function newton_solve!(b::B200ImplicitTrajectory, p::CI.CIMPC, q0, q1, u_out; ac
         warm_start::Bool = true, info = nothing, stream = C_NULL)
     H = p.H_mpc
     ref_q = reduce(hcat, p.traj.q[1:H+2]); ref_u = reduce(hcat, p.traj.u[1:H])
+    ref_γ = reduce(hcat, p.traj.γ[1:H]); ref_b = reduce(hcat, p.traj.b[1:H])   # used in :configurationforce mode only
     μ, h = p.traj.θ[1][end-1], p.traj.h
     ptr(x) = x === nothing ? C_NULL : reinterpret(Ptr{Cvoid}, pointer(x))   # CuPtr → raw device address
-    check(b.ctx, ccall((:cimpc_newton_solve_batch, LIB), Cint,
-        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
-         Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
-        b.ctx, Int32.(p.window .- 1), ref_q, ref_u, μ, h, ptr(q0), ptr(q1), ptr(active), warm_start ? 1 : 0,
-        ptr(u_out), C_NULL, ptr(info), stream))
+    check(b.ctx, ccall((:cimpc_newton_solve_batch_ex, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Cvoid},
+         Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+        b.ctx, Int32.(p.window .- 1), ref_q, ref_u, ref_γ, ref_b, μ, h, ptr(q0), ptr(q1), ptr(active), warm_start ? 1 : 0,
+        ptr(u_out), C_NULL, C_NULL, ptr(info), stream))
 end
 
 """
