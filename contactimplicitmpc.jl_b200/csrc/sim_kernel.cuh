@@ -47,7 +47,7 @@ struct SimParams {
   double* b_out;      // nb × R
   uint8_t* status;    // R
   int32_t* iters;     // R
-  double* scratch;    // per warp tile: (2·NZ + NTH + NNZ + NZ) × 32 doubles
+  double* scratch;    // per tile of 32 rollouts: SimLayout::TILE × 32 doubles
 };
 
 template <class GEN>
@@ -59,7 +59,9 @@ struct SimLayout {
   static constexpr int NTRIG = GEN::NTRIG, NTRIG_VAR = GEN::NTRIG_VAR;
   static constexpr int O_Z = 0, O_TH = O_Z + NZ, O_R = O_TH + NTH, O_D = O_R + NZ, O_J = O_D + NZ;
   static constexpr int O_TR = O_J + NNZ;  // sin / cos of the trig atoms
-  static constexpr int TILE = O_TR + 2 * NTRIG;
+  static constexpr int O_R2 = O_TR + 2 * NTRIG;  // thread-per-trial line search: residuals and z-dependent atoms of the trials
+  static constexpr int O_TR2 = O_R2 + NZ;
+  static constexpr int TILE = O_TR2 + 2 * NTRIG_VAR;
   // shared memory per warp (doubles): K, rhs/solution ×2, ry2, ŷ1, ŷ2, y1, y2, perm
   static constexpr int O_LINE = (NK * LD + 1) & ~1;        // pivot-row line of the register LU (16-byte aligned)
   static constexpr int O_RHS = O_LINE + ((NK + 2) & ~1);
@@ -254,27 +256,50 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
   bool done = !valid;
   int iters = 0;
   for (int it = 0;; ++it) {
-    // ---- candidate + back-tracking on the violations (slice per warp, thread per rollout) ----
+    // ---- candidate + back-tracking on the violations ----
+    // Two mappings of the same generated code (ONE call site):
+    //   * thread per rollout (the normal case): trial `ls` of every rollout that has not accepted yet, one pass per ls;
+    //   * thread per TRIAL: when at most two rollouts of the tile are still back-tracking, lane l evaluates trial
+    //     ls + l of ONE of them, so all remaining trials cost one pass.  A stalled rollout (every trial rejected, the
+    //     last one taken unconditionally: max_ls + 1 = 26 residual evaluations per iteration, 100 iterations) used to
+    //     set the duration of the whole launch; the first acceptable trial is the one the sequential search would stop
+    //     at, so the result is identical.
     {
       const double rv0 = r_vio, kv0 = k_vio;
       bool acc = done && it > 0;
-      for (int ls = 0; ls <= o.max_ls; ++ls) {
-        const bool ev = !acc;
-        auto zc = [&](int i) { return alpha == 0.0 ? S(L::O_Z, i) : S(L::O_Z, i) - alpha * S(L::O_D, i); };
-        // trig atoms of the candidate point (the θ-only ones once)
+      int ls = 0;  // next trial of the thread-per-rollout mapping (uniform)
+      for (;;) {
+        const unsigned pend = __ballot_sync(FULLM, !acc);  // identical in every warp
+        if (pend == 0u) break;
+        const int ntr = o.max_ls - ls + 1;                  // trials ls .. max_ls
+        const bool par = ls >= 1 && __popc(pend) <= 2 && ntr <= 32;
+        const int jj = par ? __ffs(pend) - 1 : lane;        // column whose z, Δ, θ this lane reads
+        double a_l = __shfl_sync(FULLM, alpha, jj);         // thread per rollout: jj = lane, a_l = alpha
+        bool ev = !acc;
+        int o_r = L::O_R, o_tr = L::O_TR;
+        if (par) {
+          for (int k = 0; k < lane && k < ntr - 1; ++k) a_l *= o.ls_scale;  // the same products the sequential search forms
+          ev = lane < ntr;
+          o_r = L::O_R2;
+          o_tr = L::O_TR2;
+        }
+        auto zc = [&](int i) { return a_l == 0.0 ? Sj(L::O_Z, i, jj) : Sj(L::O_Z, i, jj) - a_l * Sj(L::O_D, i, jj); };
+        auto thc = [&](int i) { return Sj(L::O_TH, i, jj); };
+        auto trc = [&](int i) { return (i < 2 * L::NTRIG_VAR) ? S(o_tr, i) : Sj(L::O_TR, i, jj); };
+        // trig atoms of the candidate point (the θ-only ones once per rollout, on trip 0)
         if (ev) {
           for (int k = wid; k < (it == 0 ? L::NTRIG : L::NTRIG_VAR); k += WARPS) {
             double sn, cs;
-            sincos(GEN::trig_arg(k, zc, th), &sn, &cs);
-            S(L::O_TR, 2 * k) = sn;
-            S(L::O_TR, 2 * k + 1) = cs;
+            sincos(GEN::trig_arg(k, zc, thc), &sn, &cs);
+            S(o_tr, 2 * k) = sn;
+            S(o_tr, 2 * k + 1) = cs;
           }
         }
         __syncthreads();
         double rv = 0.0, kv = 0.0;
         if (ev) {
-          GEN::r_slice(wid, zc, th, tr, 0.0, [&](int i, double v) {
-            S(L::O_R, i) = v;
+          GEN::r_slice(wid, zc, thc, trc, 0.0, [&](int i, double v) {
+            S(o_r, i) = v;
             if (i < NX + NY) rv = fmax(rv, fabs(v));
             else kv = fmax(kv, fabs(v));
           });
@@ -289,13 +314,30 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
           kv = fmax(kv, part_kv[w * 32 + lane]);
         }
         __syncthreads();
-        if (ev) {
-          r_vio = rv;
-          k_vio = kv;
-          if (rv <= rv0 || kv <= kv0 || ls == o.max_ls) acc = true;
-          else alpha *= o.ls_scale;
+        if (!par) {
+          if (ev) {
+            r_vio = rv;
+            k_vio = kv;
+            if (rv <= rv0 || kv <= kv0 || ls == o.max_ls) acc = true;
+            else alpha *= o.ls_scale;
+          }
+          ++ls;
+        } else {
+          // first acceptable trial of rollout jj (the last one is taken unconditionally), adopted by its mirror lanes
+          const double rv0j = __shfl_sync(FULLM, rv0, jj), kv0j = __shfl_sync(FULLM, kv0, jj);
+          const bool okl = ev && (rv <= rv0j || kv <= kv0j || lane == ntr - 1);
+          const int w = __ffs(__ballot_sync(FULLM, okl)) - 1;
+          const double rvw = __shfl_sync(FULLM, rv, w), kvw = __shfl_sync(FULLM, kv, w), aw = __shfl_sync(FULLM, a_l, w);
+          if (lane == jj) {
+            r_vio = rvw;
+            k_vio = kvw;
+            alpha = aw;
+            acc = true;
+          }
+          for (int e = threadIdx.x; e < NZ; e += WARPS * 32) Sj(L::O_R, e, jj) = Sj(L::O_R2, e, w);
+          for (int e = threadIdx.x; e < 2 * L::NTRIG_VAR; e += WARPS * 32) Sj(L::O_TR, e, jj) = Sj(L::O_TR2, e, w);
+          __syncthreads();
         }
-        if (__all_sync(FULLM, acc)) break;  // identical in every warp
       }
       if (it > 0 && !done) {
         for (int e = wid; e < NZ; e += WARPS) S(L::O_Z, e) -= alpha * S(L::O_D, e);

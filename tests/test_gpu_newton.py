@@ -243,3 +243,67 @@ def test_general_kernel_equals_specialised_kernel(cuda_device):
     assert same.mean() >= 0.95
     assert np.abs(res[0][0][same] - res[1][0][same]).max() <= 1e-8
     assert np.abs(res[0][1][same] - res[1][1][same]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("robot,H,kappa", [("hopper_2D", 10, 2.0e-4), ("centroidal_quadruped", 20, 2.0e-4)])
+def test_newton_other_robots_match_oracle(cuda_device, robot, H, kappa):
+    """The specialised device Newton on the other two BASELINE robots (hopper: examples/hopper/flat.jl:24-51, H_mpc = 10;
+    centroidal quadruped: examples/centroidal_quadruped/flat_trot.jl:31-62, H_mpc = 20) against the numpy oracle."""
+    import torch
+    import cimpc_b200 as cb
+    from oracle.newton import TrackingObjective
+    m, lin, gait, ref = _reference_traj(robot)
+    rng = np.random.default_rng(41)
+    oq = np.tile(1e-1 * (0.5 + rng.random(m.nq)), (H, 1))
+    ou = np.tile(1e-1 * (0.5 + rng.random(m.nu)), (H, 1))
+    obj = TrackingObjective(q=oq, u=ou, gamma=np.full((H, m.nc), 1e-100), b=np.full((H, m.nb), 1e-100))
+    ip_kw = dict(r_tol=1e-8, kappa_tol=kappa, max_iter=100, max_ls=0, undercut=5.0)
+    n_opts = dict(r_tol=3e-4, max_iter=5)
+    R = 6
+    q0 = np.tile(ref.q[0], (R, 1))
+    q1 = ref.q[1] + 0.003 * rng.standard_normal((R, m.nq))
+    window = np.arange(H + 2, dtype=np.int32)
+    im = cb.ImplicitTrajectory(*SIZES[robot], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"], mode="configuration",
+                               opts=cb.InteriorPointOptions(diff_sol=True, **ip_kw))
+    nw = cb.Newton(im, H, R, oq, ou, kappa, cb.NewtonOptions(**n_opts))
+    mu = float(lin["th0"][0, -2])
+    u, q, info = nw.solve(window, ref.q[:H + 2], ref.u[:H], mu, gait["h"], torch.from_numpy(q0).to(cuda_device),
+                          torch.from_numpy(q1).to(cuda_device), want_q=True)
+    torch.cuda.synchronize()
+    u, q, info = u.cpu().numpy(), q.cpu().numpy(), info.cpu().numpy()
+    agree, worst = 0, 0.0
+    for r in range(R):
+        core, dyn = _oracle_newton_general(robot, "configuration", m, lin, gait, H, obj, kappa, ip_kw, n_opts)
+        uo = core.solve(dyn, q0[r], q1[r], list(window), ref, warm_start=False)
+        if core.stats["iters"] == info[r, 0] and core.stats["ip_sweeps"] == info[r, 1]:
+            agree += 1
+            worst = max(worst, np.abs(u[r] - uo).max() / max(1.0, np.abs(uo).max()), np.abs(q[r] - core.traj.q).max())
+    assert agree >= R - 1, f"only {agree}/{R} rollouts followed the oracle's iteration path"
+    assert worst <= 1e-6, worst
+
+
+def test_newton_entry_points_reject_bad_arguments(cuda_device):
+    """Error behaviour at the ABI: nothing throws inside the library, every misuse is a status code."""
+    import ctypes as C
+    import cimpc_b200 as cb
+    from cimpc_b200 import package
+    capi = package.capi
+    m, lin, gait, ref = _reference_traj("flamingo")
+    H = 15
+    im = cb.ImplicitTrajectory(*SIZES["flamingo"], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
+                               mode="configurationforce", opts=cb.InteriorPointOptions(diff_sol=True))
+    oq, ou = np.ones((H, m.nq)), np.ones((H, m.nu))
+    with pytest.raises(ValueError):  # host mirror: force mode needs the γ, b weights
+        cb.Newton(im, H, 4, oq, ou, 2e-4)
+    with pytest.raises(cb.CimpcError) as e:  # force weights that are not negligible: unsupported, not silently wrong
+        cb.Newton(im, H, 4, oq, ou, 2e-4, obj_gamma=np.full((H, m.nc), 1e-3), obj_b=np.full((H, m.nb), 1e-100))
+    assert e.value.code == 2
+    with pytest.raises(cb.CimpcError) as e:  # non-positive velocity weight
+        cb.Newton(im, H, 4, oq, ou, 2e-4, obj_gamma=np.full((H, m.nc), 1e-100), obj_b=np.full((H, m.nb), 1e-100),
+                  obj_v=np.zeros((H, m.nq)))
+    assert e.value.code == 1
+    # the :configuration-only entry point refuses a :configurationforce context
+    lib = capi.load_library()
+    no, io = cb.NewtonOptions().to_c(), cb.InteriorPointOptions().to_c()
+    rc = lib.cimpc_newton_create(im._ctx, H, 4, oq.ctypes.data, ou.ctypes.data, 2e-4, C.byref(no), C.byref(io))
+    assert rc == 2
