@@ -73,7 +73,7 @@ struct NewtonSmem {
   // per-warp shared memory (doubles): candidate q, u, ν; rhs/solution; d; r_x; Q⁻¹; six sliding-window
   // factor blocks; a three-stage window of δz blocks
   __host__ __device__ static constexpr int per_warp(int H) {
-    return (H + 2) * NQ + H * NU + 3 * H * ND + 2 * H * (NU + NQ) + 6 * BS + 3 * ND * NCOL + 8;
+    return (H + 2) * NQ + H * NU + 3 * H * ND + 2 * H * (NU + NQ) + 6 * BS + 3 * ND * NCOL + 3 * ND + 8;
   }
   // global scratch per rollout: the three block columns L_tt, L_{t+1,t}, L_{t+2,t} of every stage
   __host__ __device__ static constexpr size_t l_doubles(int H) { return (size_t)H * 3 * BS; }
@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
   double* qi = rx + H * NR;             // H×NR   Q⁻¹ (diagonal)
   double* blk = qi + H * NR;            // 6 factor blocks
   double* zwin = blk + 6 * BS;          // δz of stages t, t+1, t+2 (ring of 3)
+  double* colb = zwin + 3 * ND * NCOL;  // 2×ND  column of the Cholesky step in flight (double-buffered by parity)
+  double* rdg = colb + 2 * ND;          // ND    reciprocals of the diagonal of L_tt
 
   const double* cand_q = p.cand_q + (size_t)r * (H + 2) * NQ;
   const double* cand_u = p.cand_u + (size_t)r * H * NU;
@@ -283,49 +285,73 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
         if (t + 2 < H) A2[e] = -ZW(t + 2, b, a) * QIq(t, b);
       }
       __syncwarp();
-      // ---- potrf: A0 = L Lᵀ in place (lane = row) ----
-      for (int j = 0; j < ND; ++j) {
-        const double djj = sqrt(A0[j + j * ND]);
-        const double inv = 1.0 / djj;
-        __syncwarp();
-        if (lane == j) A0[j + j * ND] = djj;
-        if (lane > j && lane < ND) A0[lane + j * ND] *= inv;
-        __syncwarp();
-        if (lane > j && lane < ND) {
-          const double laj = A0[lane + j * ND];
-          for (int c = j + 1; c <= lane; ++c) A0[lane + c * ND] = fma(-laj, A0[c + j * ND], A0[lane + c * ND]);
+      // ---- potrf: A0 = L Lᵀ, lane = row, the row lives in REGISTERS; one published column + ≤ ND−1 FMAs per step
+      //      (v1 did a read-modify-write of shared memory per element: 4× the dependent latency) ----
+      {
+        double rw[ND];
+#pragma unroll
+        for (int c = 0; c < ND; ++c) rw[c] = (lane < ND && c <= lane) ? A0[lane + c * ND] : 0.0;
+#pragma unroll
+        for (int j = 0; j < ND; ++j) {
+          const double ajj = __shfl_sync(FULLM, rw[j], j);
+          const double inv = rsqrt(ajj);  // 1 / l_jj
+          const double lij = (lane == j) ? ajj * inv : rw[j] * inv;
+          rw[j] = lij;
+          double* cb = colb + (j & 1) * ND;
+          if (lane >= j && lane < ND) cb[lane] = lij;
+          if (lane == j) rdg[j] = inv;
+          __syncwarp();
+#pragma unroll
+          for (int c = j + 1; c < ND; ++c)
+            if (c <= lane) rw[c] = fma(-lij, cb[c], rw[c]);
         }
-        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < ND; ++c)
+          if (lane < ND && c <= lane) A0[lane + c * ND] = rw[c];
       }
-      // ---- trsm: A1 ← A1 L⁻ᵀ, A2 ← A2 L⁻ᵀ (lane = row of [A1; A2]); forward substitution for y_t ----
+      __syncwarp();
+      // ---- trsm: A1 ← A1 L⁻ᵀ, A2 ← A2 L⁻ᵀ (one row of [A1; A2] per lane pass, the row in registers);
+      //      forward substitution for y_t ----
       {
         const int nrows = (t + 1 < H ? ND : 0) + (t + 2 < H ? ND : 0);
-        if (lane < nrows) {
-          double* X = (lane < ND) ? (A1 + lane) : (A2 + lane - ND);
+        for (int row = lane; row < nrows; row += 32) {
+          double* X = (row < ND) ? (A1 + row) : (A2 + row - ND);
+          double x[ND];
+#pragma unroll
+          for (int c = 0; c < ND; ++c) x[c] = X[c * ND];
+#pragma unroll
           for (int c = 0; c < ND; ++c) {
-            double s = X[c * ND];
-            for (int k = 0; k < c; ++k) s = fma(-X[k * ND], A0[c + k * ND], s);
-            X[c * ND] = s / A0[c + c * ND];
+            double sacc = x[c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) sacc = fma(-x[k], A0[c + k * ND], sacc);
+            x[c] = sacc * rdg[c];
           }
+#pragma unroll
+          for (int c = 0; c < ND; ++c) X[c * ND] = x[c];
         }
         __syncwarp();
-        // y_t = L_tt⁻¹ (g_t − L_{t,t−1} y_{t−1} − L_{t,t−2} y_{t−2})
-        if (lane < ND) {
-          double s = gv[t * ND + lane];
-          if (t >= 1)
-            for (int k = 0; k < ND; ++k) s = fma(-P1[lane + k * ND], gv[(t - 1) * ND + k], s);
-          if (t >= 2)
-            for (int k = 0; k < ND; ++k) s = fma(-Q2[lane + k * ND], gv[(t - 2) * ND + k], s);
-          gv[t * ND + lane] = s;
+        // y_t = L_tt⁻¹ (g_t − L_{t,t−1} y_{t−1} − L_{t,t−2} y_{t−2}): the right-hand side stays in a register of its
+        // row's lane, y_c travels by shuffle (no shared-memory round trip and no __syncwarp per step)
+        {
+          double sreg = 0.0, lrow[ND];
+          if (lane < ND) {
+            sreg = gv[t * ND + lane];
+            if (t >= 1)
+              for (int k = 0; k < ND; ++k) sreg = fma(-P1[lane + k * ND], gv[(t - 1) * ND + k], sreg);
+            if (t >= 2)
+              for (int k = 0; k < ND; ++k) sreg = fma(-Q2[lane + k * ND], gv[(t - 2) * ND + k], sreg);
+          }
+          const double rdl = (lane < ND) ? rdg[lane] : 0.0;
+#pragma unroll
+          for (int c = 0; c < ND; ++c) lrow[c] = (lane < ND && c < lane) ? A0[lane + c * ND] : 0.0;
+#pragma unroll
+          for (int c = 0; c < ND; ++c) {
+            const double yc = __shfl_sync(FULLM, sreg * rdl, c);
+            sreg = (lane == c) ? yc : fma(-lrow[c], yc, sreg);  // lrow[c] = 0 for the rows above c
+          }
+          if (lane < ND) gv[t * ND + lane] = sreg;
         }
         __syncwarp();
-        for (int c = 0; c < ND; ++c) {
-          const double yc = gv[t * ND + c] / A0[c + c * ND];
-          __syncwarp();
-          if (lane == c) gv[t * ND + c] = yc;
-          if (lane > c && lane < ND) gv[t * ND + lane] = fma(-A0[lane + c * ND], yc, gv[t * ND + lane]);
-          __syncwarp();
-        }
       }
       // ---- keep the block column for the backward pass, slide the window ----
       for (int e = lane; e < BS; e += 32) {
@@ -343,27 +369,33 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
       A2 = oldQ2;
     }
     // ---- backward: Δν_t = L_tt⁻ᵀ (y_t − L_{t+1,t}ᵀ Δν_{t+1} − L_{t+2,t}ᵀ Δν_{t+2}) ----
+    // The three factor blocks of a stage are one contiguous run of the scratch: one coalesced copy into the (now idle)
+    // block area, then the same register / shuffle substitution as in the forward pass.
     for (int t = H - 1; t >= 0; --t) {
-      const double* L0 = Ls + (size_t)(3 * t) * BS;
-      const double* L1 = L0 + BS;
-      const double* L2 = L0 + 2 * BS;
-      for (int e = lane; e < BS; e += 32) A0[e] = L0[e];
-      if (lane < ND) {
-        double s = gv[t * ND + lane];
-        if (t + 1 < H)
-          for (int k = 0; k < ND; ++k) s = fma(-L1[k + lane * ND], gv[(t + 1) * ND + k], s);
-        if (t + 2 < H)
-          for (int k = 0; k < ND; ++k) s = fma(-L2[k + lane * ND], gv[(t + 2) * ND + k], s);
-        gv[t * ND + lane] = s;
-      }
+      const double* Lg = Ls + (size_t)(3 * t) * BS;
+      const int nblk = 1 + (t + 1 < H ? 1 : 0) + (t + 2 < H ? 1 : 0);
+      for (int e = lane; e < nblk * BS; e += 32) blk[e] = Lg[e];
       __syncwarp();
-      for (int c = ND - 1; c >= 0; --c) {
-        const double xc = gv[t * ND + c] / A0[c + c * ND];
-        __syncwarp();
-        if (lane == c) gv[t * ND + c] = xc;
-        if (lane < c) gv[t * ND + lane] = fma(-A0[c + lane * ND], xc, gv[t * ND + lane]);
-        __syncwarp();
+      const double *L0 = blk, *L1 = blk + BS, *L2 = blk + 2 * BS;
+      double sreg = 0.0, rdl = 0.0, lcol[ND];
+      if (lane < ND) {
+        sreg = gv[t * ND + lane];
+        if (t + 1 < H)
+          for (int k = 0; k < ND; ++k) sreg = fma(-L1[k + lane * ND], gv[(t + 1) * ND + k], sreg);
+        if (t + 2 < H)
+          for (int k = 0; k < ND; ++k) sreg = fma(-L2[k + lane * ND], gv[(t + 2) * ND + k], sreg);
+        rdl = 1.0 / L0[lane + lane * ND];
       }
+#pragma unroll
+      for (int c = 0; c < ND; ++c) lcol[c] = (lane < ND && c > lane) ? L0[c + lane * ND] : 0.0;
+#pragma unroll
+      for (int cc = 0; cc < ND; ++cc) {
+        const int c = ND - 1 - cc;
+        const double xc = __shfl_sync(FULLM, sreg * rdl, c);
+        sreg = (lane == c) ? xc : fma(-lcol[c], xc, sreg);  // lcol[c] = 0 for the rows below c
+      }
+      if (lane < ND) gv[t * ND + lane] = sreg;
+      __syncwarp();
     }
     // Δx = Q⁻¹ (r_x − Cᵀ Δν);  Δ = [Δu, Δq, Δν] per stage
     for (int e = lane; e < H * NR; e += 32) {
