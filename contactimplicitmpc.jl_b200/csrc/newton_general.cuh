@@ -37,7 +37,7 @@ struct NewtonGSmem {
     return (H + 2) * NQ + H * NU + H * ND + H * NYD   // candidate q, u, ν, y
            + H * NB + H * ND + 2 * H * NRX + H * NYD  // g → μ ; d ; r_x ; Q⁻¹ ; r_y → Δν^y
            + (VEL ? H * NQ : 0)                       // V⁻¹
-           + 6 * BS + 3 * ND * NCOL + 8;
+           + 6 * BS + 3 * ND * NCOL + 3 * NB + 8;     // factor blocks, δz window, Cholesky column (×2) + reciprocal diagonal
   }
   __host__ __device__ static constexpr size_t l_doubles(int H) { return (size_t)H * 3 * BS; }
 };
@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(THREADS) newton_step_general_kernel(const Newt
   double* vi = ry + H * NYD;            // H×NQ    V⁻¹ (VEL)
   double* blk = vi + (VEL ? H * NQ : 0);  // 6 factor blocks
   double* zwin = blk + 6 * BS;          // δz of stages t, t+1, t+2 (ring of 3)
+  double* colb = zwin + 3 * ND * NCOL;  // 2×NB  column of the Cholesky step in flight (double-buffered by parity)
+  double* rdg = colb + 2 * NB;          // NB    reciprocals of the diagonal of L_tt
 
   const double* cand_q = p.cand_q + (size_t)r * (H + 2) * NQ;
   const double* cand_u = p.cand_u + (size_t)r * H * NU;
@@ -303,30 +305,66 @@ __global__ void __launch_bounds__(THREADS) newton_step_general_kernel(const Newt
         }
       }
       __syncwarp();
-      // ---- potrf: A0 = L Lᵀ in place ----
-      for (int j = 0; j < NB; ++j) {
-        const double djj = sqrt(A0[j + j * NB]);
-        const double inv = 1.0 / djj;
-        __syncwarp();
-        if (lane == 0) A0[j + j * NB] = djj;
-        for (int i = j + 1 + lane; i < NB; i += 32) A0[i + j * NB] *= inv;
-        __syncwarp();
-        for (int i = j + 1 + lane; i < NB; i += 32) {
-          const double laj = A0[i + j * NB];
-          for (int c = j + 1; c <= i; ++c) A0[i + c * NB] = fma(-laj, A0[c + j * NB], A0[i + c * NB]);
+      // ---- potrf: A0 = L Lᵀ with the rows in registers (row i of lane i, and row 32 + i when NB > 32), one published
+      //      column per step; trsm rows and the forward substitution in registers / by shuffle (as newton_kernel.cuh) ----
+      {
+        constexpr int RPL = (NB + 31) / 32;  // rows per lane
+        double rw[RPL][NB];
+#pragma unroll
+        for (int q_ = 0; q_ < RPL; ++q_)
+#pragma unroll
+          for (int c = 0; c < NB; ++c) {
+            const int i = lane + 32 * q_;
+            rw[q_][c] = (i < NB && c <= i) ? A0[i + c * NB] : 0.0;
+          }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          const double ajj = __shfl_sync(FULLM, rw[j / 32][j], j % 32);
+          const double inv = rsqrt(ajj);
+          double* cb = colb + (j & 1) * NB;
+#pragma unroll
+          for (int q_ = 0; q_ < RPL; ++q_) {
+            const int i = lane + 32 * q_;
+            const double lij = (i == j) ? ajj * inv : rw[q_][j] * inv;
+            rw[q_][j] = lij;
+            if (i >= j && i < NB) cb[i] = lij;
+          }
+          if (lane == 0) rdg[j] = inv;
+          __syncwarp();
+#pragma unroll
+          for (int q_ = 0; q_ < RPL; ++q_) {
+            const int i = lane + 32 * q_;
+            const double lij = rw[q_][j];
+#pragma unroll
+            for (int c = j + 1; c < NB; ++c)
+              if (c <= i && i < NB) rw[q_][c] = fma(-lij, cb[c], rw[q_][c]);
+          }
         }
-        __syncwarp();
+#pragma unroll
+        for (int q_ = 0; q_ < RPL; ++q_)
+#pragma unroll
+          for (int c = 0; c < NB; ++c) {
+            const int i = lane + 32 * q_;
+            if (i < NB && c <= i) A0[i + c * NB] = rw[q_][c];
+          }
       }
-      // ---- trsm: A1 ← A1 L⁻ᵀ, A2 ← A2 L⁻ᵀ (one row of [A1; A2] per lane pass); forward substitution ----
+      __syncwarp();
       {
         const int nrows = (t + 1 < H ? NB : 0) + (t + 2 < H ? NB : 0);
         for (int row = lane; row < nrows; row += 32) {
           double* X = (row < NB) ? (A1 + row) : (A2 + row - NB);
+          double x[NB];
+#pragma unroll
+          for (int c = 0; c < NB; ++c) x[c] = X[c * NB];
+#pragma unroll
           for (int c = 0; c < NB; ++c) {
-            double s = X[c * NB];
-            for (int k = 0; k < c; ++k) s = fma(-X[k * NB], A0[c + k * NB], s);
-            X[c * NB] = s / A0[c + c * NB];
+            double sacc = x[c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) sacc = fma(-x[k], A0[c + k * NB], sacc);
+            x[c] = sacc * rdg[c];
           }
+#pragma unroll
+          for (int c = 0; c < NB; ++c) X[c * NB] = x[c];
         }
         __syncwarp();
         for (int i = lane; i < NB; i += 32) {
@@ -339,7 +377,7 @@ __global__ void __launch_bounds__(THREADS) newton_step_general_kernel(const Newt
         }
         __syncwarp();
         for (int c = 0; c < NB; ++c) {
-          const double yc = gv[t * NB + c] / A0[c + c * NB];
+          const double yc = gv[t * NB + c] * rdg[c];
           __syncwarp();
           if (lane == 0) gv[t * NB + c] = yc;
           for (int i = c + 1 + lane; i < NB; i += 32) gv[t * NB + i] = fma(-A0[i + c * NB], yc, gv[t * NB + i]);
@@ -366,6 +404,7 @@ __global__ void __launch_bounds__(THREADS) newton_step_general_kernel(const Newt
       const double* L1 = L0 + BS;
       const double* L2 = L0 + 2 * BS;
       for (int e = lane; e < BS; e += 32) A0[e] = L0[e];
+      for (int i = lane; i < NB; i += 32) rdg[i] = 1.0 / L0[i + i * NB];
       for (int i = lane; i < NB; i += 32) {
         double s = gv[t * NB + i];
         if (t + 1 < H)
@@ -376,7 +415,7 @@ __global__ void __launch_bounds__(THREADS) newton_step_general_kernel(const Newt
       }
       __syncwarp();
       for (int c = NB - 1; c >= 0; --c) {
-        const double xc = gv[t * NB + c] / A0[c + c * NB];
+        const double xc = gv[t * NB + c] * rdg[c];
         __syncwarp();
         if (lane == 0) gv[t * NB + c] = xc;
         for (int i = lane; i < c; i += 32) gv[t * NB + i] = fma(-A0[c + i * NB], xc, gv[t * NB + i]);
