@@ -117,7 +117,10 @@ cudaError_t launch_linearize(const LinEvalParams& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-constexpr int IP_THREADS = 256;
+// CTA size of ip_solve_kernel.  One-subproblem-per-warp instances (G = 32: centroidal, 74 KB of staged constants) use
+// 512 threads: one CTA per SM either way, but 16 instead of 8 resident warps (the register cap of 128 costs some spills).
+template <class D>
+constexpr int ip_threads() { return D::G == 32 ? 512 : 256; }
 
 template <class D>
 LinLayout layout_of() {
@@ -131,9 +134,9 @@ LinLayout layout_of() {
 
 template <class D>
 cudaError_t prepare_ip() {  // opt in to > 48 KB of dynamic shared memory (once per instance)
-  static cudaError_t once = cudaFuncSetAttribute(ip_solve_kernel<D, IP_THREADS>,
+  static cudaError_t once = cudaFuncSetAttribute(ip_solve_kernel<D, ip_threads<D>()>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)KernelSmem<D, IP_THREADS>::BYTES);
+                                                 (int)KernelSmem<D, ip_threads<D>()>::BYTES);
   return once;
 }
 
@@ -141,14 +144,14 @@ template <class D>
 cudaError_t occupancy_ip(int* blocks_per_sm) {
   cudaError_t e = prepare_ip<D>();
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ip_solve_kernel<D, IP_THREADS>, IP_THREADS,
-                                                       KernelSmem<D, IP_THREADS>::BYTES);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ip_solve_kernel<D, ip_threads<D>()>, ip_threads<D>(),
+                                                       KernelSmem<D, ip_threads<D>()>::BYTES);
 }
 
 template <class D>
 cudaError_t launch_ip(const IpParams& p, int sm_count, cudaStream_t s) {
   constexpr int PPW = 32 / D::G;
-  constexpr int PPB = PPW * (IP_THREADS / 32);  // subproblems in flight per CTA
+  constexpr int PPB = PPW * (ip_threads<D>() / 32);  // subproblems in flight per CTA
   int occ = 1;
   cudaError_t e = occupancy_ip<D>(&occ);
   if (e != cudaSuccess) return e;
@@ -159,7 +162,7 @@ cudaError_t launch_ip(const IpParams& p, int sm_count, cudaStream_t s) {
   int64_t cap = (int64_t)sm_count * occ;
   int grid = (int)(need < cap ? need : cap);
   if (grid < 1) grid = 1;
-  ip_solve_kernel<D, IP_THREADS><<<grid, IP_THREADS, KernelSmem<D, IP_THREADS>::BYTES, s>>>(p);
+  ip_solve_kernel<D, ip_threads<D>()><<<grid, ip_threads<D>(), KernelSmem<D, ip_threads<D>()>::BYTES, s>>>(p);
   return cudaGetLastError();
 }
 
