@@ -399,8 +399,11 @@ struct KernelSmem {
   static constexpr size_t BYTES = (size_t)(D::SMEM_DOUBLES + GROUPS * GS) * 8 + 64;
 };
 
+// Two CTAs of 256 threads per SM (128 registers) for the instances that share a warp between subproblems; measured
+// alternatives on the quadruped batch: 2 × 320 threads at 96 registers 61.9 M/s, 2 × 288 61.6, 3 × 192 59.6, against
+// 63.5 M/s here (the shared-memory pipe, not occupancy, is the limiter) and 44 M/s with one CTA of 148 registers.
 template <class D, int THREADS>
-__global__ void __launch_bounds__(THREADS) ip_solve_kernel(const IpParams p) {
+__global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel(const IpParams p) {
   constexpr int NX = D::NX, NY = D::NY, NTH = D::NTH, NZ = D::NZ, NC = D::NC;
   constexpr int G = D::G, PPW = 32 / G;
   using S = GroupScratch<D>;
