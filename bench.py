@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--no-mpc", action="store_true", help="skip the batched newton_solve! (MPC steps/s) leg")
     ap.add_argument("--mpc-rollouts", type=int, default=16384)
     ap.add_argument("--no-closed-loop", action="store_true", help="skip the on-device Monte-Carlo closed-loop leg")
+    ap.add_argument("--closed-loop-groups", type=int, default=2, help="independent parts (streams) of the closed-loop leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -393,9 +394,14 @@ def main():
     if not args.no_mpc and not args.no_closed_loop:
         Rc = min(args.rollouts, args.mpc_rollouts)
         N_sample = 5
-        mc = cb.MonteCarloRollouts(im, gait["q"], gait["u"], gait["mu"], 1.0, gait["h"], H_mpc=H_MPC, N_sample=N_sample,
-                                   obj_q=oq, obj_u=ou, kappa=1.0e-4, n_rollouts=Rc,
-                                   newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5))
+        # the rollouts run as `--closed-loop-groups` independent parts (own stream + host thread each): one part's
+        # simulator latency tail overlaps the other parts' work; per-rollout results do not depend on the split
+        def make_im():
+            return cb.ImplicitTrajectory(*SIZES[ROBOT], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"], mode=MODE,
+                                         opts=opts, device=dev.index or 0)
+        mc = cb.GroupedRollouts(make_im, Rc, args.closed_loop_groups, gait["q"], gait["u"], gait["mu"], 1.0, gait["h"],
+                                H_mpc=H_MPC, N_sample=N_sample, obj_q=oq, obj_u=ou, kappa=1.0e-4,
+                                newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5))
         lo, hi = cb.shard_rollouts(Rc * world, world, rank)
         qinit = cb.quadruped_initial_configurations(Rc * world, seed=100)[lo:hi]
         q1c = torch.from_numpy(qinit).to(dev)
@@ -424,7 +430,7 @@ def main():
             gathered = list(res_c["q"].permute(1, 0, 2).shape)
         closed = {"value": Rc * world * mc.mpc_steps / (float(tc.item()) * 1e-3), "unit": "MPC steps/s (closed loop)",
                   "rollouts_per_gpu": Rc, "sim_steps": H_sim_c, "mpc_steps_per_rollout": mc.mpc_steps,
-                  "ms_total": float(tc.item()), "sim_ok_frac": float(okc.item()),
+                  "ms_total": float(tc.item()), "sim_ok_frac": float(okc.item()), "groups": args.closed_loop_groups,
                   "gathered_trajectory_shape": gathered,
                   "config": "examples/quadruped/monte_carlo.jl: initial configurations from the conf_min/conf_max box "
                             "(Philox seed 100), policy every 5 simulator steps, nonlinear simulator step on the device; "

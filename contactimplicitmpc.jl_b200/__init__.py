@@ -5,5 +5,5 @@ from .capi import LIB_PATH, SYMBOLS, CimpcError, load_library  # noqa: F401
 from .solver import (ImplicitTrajectory, InteriorPointOptions, Newton, NewtonOptions,  # noqa: F401
                      Simulator, implicit_dynamics, simulator_options)
 from .sharding import gather_rollout_results, shard_rollouts, sum_statistics  # noqa: F401,E402
-from .rollout import MonteCarloRollouts, ReferenceWindow, quadruped_initial_configurations  # noqa: F401,E402
+from .rollout import GroupedRollouts, MonteCarloRollouts, ReferenceWindow, quadruped_initial_configurations  # noqa: F401,E402
 from .trajectory import ContactTraj, JLD2File, load_gait, load_traj, repeat_ref_traj, save_traj, tracking_error  # noqa: F401,E402

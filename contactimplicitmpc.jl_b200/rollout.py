@@ -124,6 +124,64 @@ class MonteCarloRollouts:
         return out
 
 
+class GroupedRollouts:
+    """The same closed loop with the rollouts cut into `groups` independent parts, each with its own context, CUDA
+    stream and host thread.  Rollouts never interact, so the parts need no synchronisation; what the split buys is
+    overlap: a simulator step ends with a latency tail (the few rollouts that run to the iteration cap)
+    during which most SMs idle — with several parts in flight another part's `newton_solve!` sweep or simulator step
+    fills them.  Per-rollout arithmetic is unchanged (same kernels, same inputs).
+
+    make_im: () -> ImplicitTrajectory (one per part: the Newton state lives in the context);
+    mc_kwargs: the keyword arguments of MonteCarloRollouts except `n_rollouts`."""
+
+    def __init__(self, make_im, n_rollouts: int, groups: int, *mc_args, **mc_kwargs):
+        G = max(1, min(int(groups), int(n_rollouts)))
+        base = [(n_rollouts * g) // G for g in range(G + 1)]
+        self.bounds = [(base[g], base[g + 1]) for g in range(G)]
+        self.parts = []
+        for lo, hi in self.bounds:
+            im = make_im()
+            self.parts.append(MonteCarloRollouts(im, *mc_args, n_rollouts=hi - lo, **mc_kwargs))
+        self.mpc_steps = 0
+
+    @property
+    def launch_count(self) -> int:
+        return sum(p.im.launch_count for p in self.parts)
+
+    def run(self, q1, v1, H_sim, record_every: int = 1):
+        import threading
+        import torch
+        main = torch.cuda.current_stream(q1.device)
+        streams = [torch.cuda.Stream(device=q1.device) for _ in self.parts]
+        outs, errs = [None] * len(self.parts), [None] * len(self.parts)
+
+        def work(g):
+            try:
+                lo, hi = self.bounds[g]
+                torch.cuda.set_device(q1.device)
+                streams[g].wait_stream(main)
+                with torch.cuda.stream(streams[g]):
+                    outs[g] = self.parts[g].run(q1[lo:hi].contiguous(), v1[lo:hi].contiguous(), H_sim, record_every)
+            except BaseException as e:  # re-raised in the caller's thread
+                errs[g] = e
+
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(len(self.parts))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+        for s_ in streams:
+            main.wait_stream(s_)
+        self.mpc_steps = self.parts[0].mpc_steps
+        out = {k: torch.cat([o[k] for o in outs], dim=1) for k in ("q", "u", "gamma", "b")}
+        out["status"] = torch.cat([o["status"] for o in outs])
+        out["failed_at"] = torch.cat([o["failed_at"] for o in outs])
+        return out
+
+
 def quadruped_initial_configurations(n: int, seed: int = 100, l_thigh: float = 0.2, l_calf: float = 0.2) -> np.ndarray:
     """`collect_runs` / `initial_configuration` of examples/quadruped/monte_carlo.jl:76-116: n initial
     configurations drawn uniformly from the box conf_min..conf_max (θ0, θ1, θ2, θ3, x, Δz), last parameter

@@ -100,3 +100,33 @@ def test_flamingo_closed_loop_on_device(cuda_device):
     assert (np.median(e_ok, axis=0) < band).all()
     if ok[0]:
         assert (e[0] < band).all()  # the nominal rollout = the reference's own test
+
+
+def test_grouped_rollouts_are_bit_identical(cuda_device):
+    """`GroupedRollouts` (independent parts on their own streams / host threads) changes scheduling only."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait, load_lin
+    robot = "quadruped"
+    lin, gait = load_lin(robot), load_gait(robot)
+    nq, nu = SIZES[robot][0], SIZES[robot][1]
+    R, N = 96, 5
+    opts = cb.InteriorPointOptions(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, diff_sol=True)
+    oq = np.tile(1e-2 * np.array([1.0, 0.02, 0.25] + [0.75] * (nq - 3)), (H_MPC, 1))
+    ou = np.tile(3e-2 * np.ones(nu), (H_MPC, 1))
+
+    def make_im():
+        return cb.ImplicitTrajectory(*SIZES[robot], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
+                                     mode="configuration", opts=opts)
+    q1 = torch.from_numpy(cb.quadruped_initial_configurations(R, seed=3)).to(cuda_device)
+    v1 = torch.from_numpy(np.tile((gait["q"][1] - gait["q"][0]) / gait["h"], (R, 1))).to(cuda_device)
+    outs = []
+    for G in (1, 3):
+        mc = cb.GroupedRollouts(make_im, R, G, gait["q"], gait["u"], gait["mu"], 1.0, gait["h"], H_mpc=H_MPC, N_sample=N,
+                                obj_q=oq, obj_u=ou, kappa=1e-4, newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5))
+        out = mc.run(q1, v1, 3 * N)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in out.items()})
+        assert mc.mpc_steps == 3
+    for k in ("q", "u", "gamma", "b", "status", "failed_at"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
