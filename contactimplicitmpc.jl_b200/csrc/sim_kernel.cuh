@@ -54,6 +54,7 @@ template <class GEN>
 struct SimLayout {
   static constexpr int NX = GEN::NQ, NY = 2 * GEN::NC + GEN::NB, NZ = GEN::NZ, NTH = GEN::NTH, NNZ = GEN::NNZ;
   static constexpr int NK = NX + NY;  // reduced system
+  static_assert(NY <= 32, "the generic linear-algebra path keeps one lane per y row");
   static constexpr int LD = NK | 1;  // odd leading dimension: row AND column walks are bank-conflict-free
   // scratch tile (doubles per lane): z, θ, r, Δ, rz non-zeros
   static constexpr int NTRIG = GEN::NTRIG, NTRIG_VAR = GEN::NTRIG_VAR;
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
           y1v[lane] = a; y2v[lane] = b;
           y1h[lane] = fmax(a, reg_j); y2h[lane] = fmax(b, reg_j);
         }
-        if (lane < NK) perm[lane] = lane;
+        for (int e = lane; e < NK; e += 32) perm[e] = e;  // NK may exceed the warp (centroidal: 42 rows)
         __syncwarp();
         if (lane < NY) K[(NX + lane) * LD + NX + lane] -= ry2[lane] * y2h[lane] / y1h[lane];
         // rhs: u = rdyn, v = rrst − Ry2∘rbil/ŷ1

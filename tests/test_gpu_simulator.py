@@ -8,7 +8,7 @@ from common import SIZES, load_gait
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("robot,tag", [("quadruped", None), ("hopper_2D", None), ("flamingo", None)])
+@pytest.mark.parametrize("robot,tag", [("quadruped", None), ("hopper_2D", None), ("flamingo", None), ("centroidal_quadruped", None)])
 def test_sim_step_matches_oracle(cuda_device, robot, tag):
     import torch
     import cimpc_b200 as cb
