@@ -11,6 +11,7 @@
 module CIMPCB200
 
 using ContactImplicitMPC
+import LinearAlgebra
 const CI = ContactImplicitMPC
 
 const LIB = get(ENV, "CIMPC_B200_LIB", joinpath(@__DIR__, "..", "contactimplicitmpc.jl_b200", "lib", "libcimpc_b200.so"))
@@ -239,7 +240,5 @@ function policy!(b::B200ImplicitTrajectory, p::CI.CIMPC, q0_dev, q_tp1, u_out, t
     end
     return u_out
 end
-
-import LinearAlgebra
 
 end # module

@@ -130,3 +130,59 @@ def test_grouped_rollouts_are_bit_identical(cuda_device):
         assert mc.mpc_steps == 3
     for k in ("q", "u", "gamma", "b", "status", "failed_at"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_hopper_closed_loop_on_device(cuda_device):
+    """BASELINE config 1 on the device: examples/hopper/flat.jl:24-51 (hopper_2D, gait_forward, H_mpc = 10, N_sample = 5,
+    κ_mpc = 2e-4, IP r_tol 1e-8 / κ_tol 2e-4 / undercut 5, Newton r_tol 3e-4 / max_iter 5, w = 0).  No tracking band is
+    published for this example, so the device loop is held to the all-CPU oracle loop run on the same settings."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait, load_lin
+    from oracle.c_oracle import COracle
+    from oracle.ip import IPOptions
+    from oracle.newton import Newton, NewtonOptions, TrackingObjective
+    from oracle.residual import get_residual
+    from oracle.simulator import CIMPC, simulate, tracking_error
+    from oracle.trajectory import ContactTraj
+    robot, H_mpc, N, kappa, H_sim, R = "hopper_2D", 10, 5, 2.0e-4, 500, 4
+    res = get_residual(robot)
+    m = res.model
+    lin, gait = load_lin(robot), load_gait(robot)
+    Hr = lin["z0"].shape[0]
+    ref = ContactTraj(m, Hr, gait["h"])
+    ref.q[:] = gait["q"]; ref.u[:] = gait["u"]; ref.gamma[:] = gait["gamma"]; ref.b[:] = gait["b"]
+    ref.z[:] = lin["z0"]; ref.theta[:] = lin["th0"]
+    h = gait["h"]
+    oq = np.tile(1e-1 * np.array([0.1, 3.0, 1.0, 3.0]), (H_mpc, 1))
+    ou = np.tile(np.array([1e-3, 1.0]), (H_mpc, 1))
+    ipo = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=kappa, undercut=5.0, diff_sol=True)
+    im = cb.ImplicitTrajectory(*SIZES[robot], ref.z, ref.theta, kappa=kappa, mode="configuration", opts=ipo)  # device linearization
+    mc = cb.MonteCarloRollouts(im, ref.q, ref.u, float(ref.theta[0, -2]), m.mu_world, h, H_mpc=H_mpc, N_sample=N, obj_q=oq,
+                               obj_u=ou, kappa=kappa, n_rollouts=R, newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5))
+    q1 = np.tile(ref.q[1], (R, 1))
+    v1 = np.tile((ref.q[1] - ref.q[0]) / h, (R, 1))
+    v1[1:] *= 1.0 + 0.02 * np.random.default_rng(62).standard_normal((R - 1, 1))
+    out = mc.run(torch.from_numpy(q1).to(cuda_device), torch.from_numpy(v1).to(cuda_device), H_sim)
+    torch.cuda.synchronize()
+    ok = out["status"].cpu().numpy()
+    assert ok[0], "the nominal rollout must complete"
+    q, u, gam, b = (out[k].cpu().numpy() for k in ("q", "u", "gamma", "b"))
+    e_gpu = tracking_error(ref, m, q[:, 0], u[:, 0], gam[:, 0], b[:, 0], N, idx_shift=(0,))
+    # the all-CPU oracle loop on the same settings
+    co = COracle(*SIZES[robot], lin, mode="configuration", solver="mgs")
+    oipo = IPOptions(r_tol=1e-8, kappa_tol=kappa, undercut=5.0, diff_sol=True)
+
+    def dyn(window, traj):
+        knot = np.array(window[:H_mpc], dtype=np.int32)
+        z, dz, st, _ = co.solve(knot, traj.theta[:H_mpc], traj.q[2:H_mpc + 2], oipo)
+        return z[:, :m.nq] - traj.q[2:H_mpc + 2], dz[:, :, :m.nq], dz[:, :, m.nq:2 * m.nq], dz[:, :, 2 * m.nq:]
+
+    obj = TrackingObjective(q=oq, u=ou, gamma=np.full((H_mpc, m.nc), 1e-100), b=np.full((H_mpc, m.nb), 1e-100))
+    newton = Newton(m, H_mpc, h, obj, kappa, NewtonOptions(r_tol=3e-4, max_iter=5))
+    policy = CIMPC(m, ref, newton, dyn, H_mpc, N)
+    ok_c, qc, uc, gc, bc = simulate(res, policy, q1[0], v1[0], H_sim, h / N, m.mu_world)
+    assert ok_c
+    e_cpu = tracking_error(ref, m, qc, uc, gc, bc, N, idx_shift=(0,))
+    print("hopper tracking errors (q, u, γ, b): GPU", np.round(e_gpu, 4), " CPU oracle", np.round(e_cpu, 4))
+    assert np.all(np.abs(e_gpu - e_cpu) <= 0.2 * e_cpu + 2e-3)
