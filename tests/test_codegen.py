@@ -32,7 +32,8 @@ void rth_eval(const double* z, const double* th, double* J) {
 '''
 
 
-@pytest.mark.parametrize("robot,tag", [("hopper_2D", "hopper2d"), ("quadruped", "quadruped")])
+@pytest.mark.parametrize("robot,tag", [("hopper_2D", "hopper2d"), ("quadruped", "quadruped"), ("flamingo", "flamingo"),
+                                       ("centroidal_quadruped", "centroidal")])
 def test_generated_residual_matches_oracle(tmp_path, robot, tag):
     from oracle.residual import get_residual
     hdr = os.path.join(GEN, f"residual_{tag}.h")
