@@ -171,8 +171,9 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
 /* ------------------------------------------------------------------------------------------------
  * Batched `newton_solve!` (src/controller/newton.jl:169-288) for n_rollouts Monte-Carlo rollouts that
  * track the same reference window (policy.jl:100-107, 131): one call = one MPC step of every rollout.
- * :configuration mode with a `TrackingObjective` (diagonal weights), the configuration of the
- * reference's Monte-Carlo examples (examples/quadruped/monte_carlo.jl:33-58).
+ * The first two entry points cover :configuration mode with a `TrackingObjective` (diagonal weights), the configuration
+ * of the reference's Monte-Carlo examples (examples/quadruped/monte_carlo.jl:33-58); the `_ex` forms further below add
+ * :configurationforce mode and the `TrackingVelocityObjective` (the flamingo policy, examples/flamingo/flat.jl).
  * ------------------------------------------------------------------------------------------------ */
 
 /* `NewtonOptions` (src/controller/newton.jl:2-11); `max_time` is replaced by the iteration caps. */
