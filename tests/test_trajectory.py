@@ -70,3 +70,29 @@ def test_tracking_error_matches_oracle():
     a = cb.tracking_error(ref_p, sim_q, sim_u, sim_g, sim_b, N_sample)
     b = oracle_te(ref_o, res.model, sim_q, sim_u, sim_g, sim_b, N_sample)
     assert np.allclose(a, b, rtol=1e-13, atol=0)
+
+
+def test_reference_window_matches_rot_n_stride():
+    """The product's policy glue (`rollout.py::ReferenceWindow`: `rot_n_stride!`, mpc_utils.jl:1-101, and
+    `update_window!`, policy.jl:162-171, on the shared reference incl. the contact forces used in :configurationforce
+    mode) against the oracle's restatement, over more than one gait period."""
+    import cimpc_b200 as cb
+    from oracle.models import get_model
+    from oracle.newton import get_stride, rot_n_stride, update_window
+    from oracle.trajectory import trajectory_from_gait
+    robot, H_mpc = "flamingo", 15
+    gold = load_gait(robot)
+    m = get_model(robot)
+    ref = trajectory_from_gait(m, gold)
+    pw = cb.ReferenceWindow(ref.q, ref.u, H_mpc, ref.gamma, ref.b)
+    ptraj, stride, window = ref.copy(), get_stride(m, ref), list(range(H_mpc + 2))
+    assert np.array_equal(pw.stride, stride)
+    for step in range(ref.H + 7):
+        assert list(pw.window) == window
+        assert np.array_equal(pw.q, ptraj.q) and np.array_equal(pw.u, ptraj.u)
+        assert np.array_equal(pw.gamma, ptraj.gamma) and np.array_equal(pw.b, ptraj.b)
+        pw.advance()
+        rot_n_stride(ptraj, stride)
+        window = update_window(window, ref.H)
+    pw.reset()
+    assert np.array_equal(pw.q, ref.q) and list(pw.window) == list(range(H_mpc + 2))
