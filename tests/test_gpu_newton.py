@@ -176,7 +176,8 @@ def _oracle_newton_general(robot, mode, m, lin, gait, H, obj, kappa, ip_kw, n_op
 @pytest.mark.parametrize("robot,mode,vel", [("quadruped", "configuration", True),
                                             ("flamingo", "configurationforce", False),
                                             ("flamingo", "configurationforce", True),
-                                            ("flamingo", "configuration", True)])
+                                            ("flamingo", "configuration", True),
+                                            ("centroidal_quadruped", "configuration", True)])
 def test_general_newton_matches_oracle(cuda_device, robot, mode, vel):
     """`newton_solve!` with γ, b as Newton variables (:configurationforce) and / or a TrackingVelocityObjective — the
     flamingo policy of test/controller/mpc_flamingo.jl:27-56 — against the numpy oracle (dense KKT + LAPACK)."""
