@@ -783,7 +783,6 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const doub
   const size_t need = ctx->entry->sim_scratch((int)n);
   if (ctx->sim_scratch_doubles < need) {
     if (ctx->sim_scratch) cudaFree(ctx->sim_scratch);
-  if (ctx->dense) cudaFree(ctx->dense);
     ctx->sim_scratch = nullptr; ctx->sim_scratch_doubles = 0;
     CK(cudaMalloc(&ctx->sim_scratch, need * sizeof(double)));
     ctx->sim_scratch_doubles = need;

@@ -455,7 +455,10 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
     const int64_t first = c0 + ctl[3];
     if (first >= c1) break;  // nothing left to do in this CTA's slice (CTA-uniform)
     const int kraw = p.knot[sub(first)];
-    const int kn = (kraw >= p.h_ref) ? 0 : kraw;  // range is validated by the host entry point
+    // a knot outside the uploaded reference is a caller bug: its subproblems are not solved, status 0, iters 0
+    // (the host entry point rejects it up front; the device entry point cannot look at device memory)
+    const bool bad_knot = kraw >= p.h_ref;
+    const int kn = bad_knot ? 0 : kraw;
     for (int64_t i = first + 1 + tid; i < c1; i += THREADS) {
       const int ki = p.knot[sub(i)];
       if (ki >= 0 && ki != kraw) {
@@ -466,6 +469,18 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
     __syncthreads();
     const int64_t seg_end = c0 + ctl[1];
     cur = first;
+    if (bad_knot) {  // CTA-uniform: flag the whole run and move on
+      for (int64_t i = first + tid; i < seg_end; i += THREADS) {
+        const int64_t pr = sub(i);
+        if (p.knot[pr] >= 0) {
+          p.status[pr] = 0;
+          p.iters[pr] = 0;
+        }
+      }
+      __syncthreads();
+      cur = seg_end;
+      continue;
+    }
     if (kn != staged) {  // CTA-uniform
       if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)(D::SMEM_DOUBLES * 8));

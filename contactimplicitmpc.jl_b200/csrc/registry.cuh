@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "ip_kernel.cuh"
 #include "lin_kernel.cuh"
 #include "newton_kernel.cuh"
@@ -39,6 +41,27 @@ struct ModelEntry {
 
 constexpr int NEWTON_THREADS = 32 * NEWTON_WARPS;
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is PER DEVICE and a process may hold contexts on
+// several GPUs (and drive them from several host threads: rollout.py::GroupedRollouts), so the largest size configured
+// so far is kept per device of the calling thread, under a lock.
+constexpr int MAX_DEVICES = 64;
+struct SmemOptIn {
+  std::mutex mu;
+  size_t configured[MAX_DEVICES] = {};
+  template <class K>
+  cudaError_t ensure(K kernel, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes <= configured[dev] || bytes <= 48 * 1024) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) configured[dev] = bytes;
+    return e;
+  }
+};
+
 template <class D>
 cudaError_t launch_newton_reset(const NewtonParams& p, const double* q0, const double* q1, int warm,
                                 const uint8_t* active, cudaStream_t s) {
@@ -49,13 +72,8 @@ cudaError_t launch_newton_reset(const NewtonParams& p, const double* q0, const d
 template <class D>
 cudaError_t launch_newton_step(const NewtonParams& p, double* lscratch, cudaStream_t s) {
   const size_t bytes = (size_t)NewtonSmem<D>::per_warp(p.H) * NEWTON_WARPS * sizeof(double);
-  static size_t configured = 0;
-  if (bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(newton_step_kernel<D, NEWTON_THREADS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-    configured = bytes;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt.ensure(newton_step_kernel<D, NEWTON_THREADS>, bytes); e != cudaSuccess) return e;
   const int grid = (p.R + NEWTON_WARPS - 1) / NEWTON_WARPS;
   newton_step_kernel<D, NEWTON_THREADS><<<grid, NEWTON_THREADS, bytes, s>>>(p, lscratch);
   return cudaGetLastError();
@@ -64,13 +82,8 @@ cudaError_t launch_newton_step(const NewtonParams& p, double* lscratch, cudaStre
 template <class D, bool VEL>
 cudaError_t launch_newton_step_general(const NewtonParams& p, double* lscratch, cudaStream_t s) {
   const size_t bytes = (size_t)NewtonGSmem<D, VEL>::per_warp(p.H) * NEWTON_WARPS * sizeof(double);
-  static size_t configured = 0;
-  if (bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(newton_step_general_kernel<D, VEL, NEWTON_THREADS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-    configured = bytes;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt.ensure(newton_step_general_kernel<D, VEL, NEWTON_THREADS>, bytes); e != cudaSuccess) return e;
   const int grid = (p.R + NEWTON_WARPS - 1) / NEWTON_WARPS;
   newton_step_general_kernel<D, VEL, NEWTON_THREADS><<<grid, NEWTON_THREADS, bytes, s>>>(p, lscratch);
   return cudaGetLastError();
@@ -93,13 +106,8 @@ template <class GEN>
 cudaError_t launch_sim_step(const SimParams& p, cudaStream_t s) {
   const int grid = (p.R + 31) / 32;
   const size_t bytes = SimLayout<GEN>::SMEM_DOUBLES * sizeof(double);
-  static bool configured = false;
-  if (!configured && bytes > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(sim_step_kernel<GEN, SIM_MIN_CTAS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-  }
-  configured = true;
+  static SmemOptIn opt;
+  if (cudaError_t e = opt.ensure(sim_step_kernel<GEN, SIM_MIN_CTAS>, bytes); e != cudaSuccess) return e;
   sim_step_kernel<GEN, SIM_MIN_CTAS><<<grid, GEN::NS * 32, bytes, s>>>(p);
   return cudaGetLastError();
 }
@@ -133,11 +141,9 @@ LinLayout layout_of() {
 }
 
 template <class D>
-cudaError_t prepare_ip() {  // opt in to > 48 KB of dynamic shared memory (once per instance)
-  static cudaError_t once = cudaFuncSetAttribute(ip_solve_kernel<D, ip_threads<D>()>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)KernelSmem<D, ip_threads<D>()>::BYTES);
-  return once;
+cudaError_t prepare_ip() {  // opt in to > 48 KB of dynamic shared memory (once per instance and device)
+  static SmemOptIn opt;
+  return opt.ensure(ip_solve_kernel<D, ip_threads<D>()>, KernelSmem<D, ip_threads<D>()>::BYTES);
 }
 
 template <class D>

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
         const unsigned pend = __ballot_sync(FULLM, !acc);  // identical in every warp
         if (pend == 0u) break;
         const int ntr = o.max_ls - ls + 1;                  // trials ls .. max_ls
-        const bool par = ls >= 1 && __popc(pend) <= 2 && ntr <= 32;
+        const bool par = it > 0 && ls >= 1 && __popc(pend) <= 2 && ntr <= 32;  // trip 0 also evaluates the θ-only atoms, which only fit O_TR
         const int jj = par ? __ffs(pend) - 1 : lane;        // column whose z, Δ, θ this lane reads
         double a_l = __shfl_sync(FULLM, alpha, jj);         // thread per rollout: jj = lane, a_l = alpha
         bool ev = !acc;

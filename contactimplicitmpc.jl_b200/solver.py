@@ -147,8 +147,9 @@ class ImplicitTrajectory:
         if alt is not None:
             alt = _f64(alt, (n, self.nc))
             alt_p = alt.ctypes.data
-        z = np.empty((n, self.nz))
-        dz = np.empty((n, self.ncol, self.nd)) if o.diff_sol else None
+        # skipped subproblems (knot = −1) leave their rows untouched: zero-filled, status 0
+        z = np.zeros((n, self.nz))
+        dz = np.zeros((n, self.ncol, self.nd)) if o.diff_sol else None
         status = np.zeros(n, dtype=np.uint8)
         iters = np.zeros(n, dtype=np.int32)
         co = o.to_c()
@@ -194,10 +195,11 @@ class ImplicitTrajectory:
             assert alt.dtype == torch.float64 and alt.is_contiguous() and alt.shape == (n, self.nc)
         dev = theta.device
         if out is None:
-            z = torch.empty((n, self.nz), dtype=torch.float64, device=dev)
-            dz = torch.empty((n, self.ncol, self.nd), dtype=torch.float64, device=dev) if o.diff_sol else None
-            status = torch.empty(n, dtype=torch.uint8, device=dev)
-            iters = torch.empty(n, dtype=torch.int32, device=dev)
+            # skipped subproblems (knot = −1) leave their rows untouched: zero-filled, status 0
+            z = torch.zeros((n, self.nz), dtype=torch.float64, device=dev)
+            dz = torch.zeros((n, self.ncol, self.nd), dtype=torch.float64, device=dev) if o.diff_sol else None
+            status = torch.zeros(n, dtype=torch.uint8, device=dev)
+            iters = torch.zeros(n, dtype=torch.int32, device=dev)
         else:
             z, dz, status, iters = out
         if stream is None:
