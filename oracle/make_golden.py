@@ -54,8 +54,29 @@ def hopper():
     print("hopper_2D H =", H, "max ||r(z_t, θ_t, 0)|| =", worst)
 
 
+# extra reference gaits kept only as MODEL PINS (tests/test_model_pins.py): a stand pins mass, gravity, B_func and the
+# contact stack unambiguously; inplace_trot_v0 was generated with the undamped model and pins the translational rows.
+# (Of the quadruped gaits only gait2 — the one the reference's tests use — satisfies the identity with the shipped model:
+# gait1 0.65, gait3 0.42, calipso_gait8 2.9, calipso_gait11 4.4 — generated with other model versions.)
+PIN_GAITS = {
+    "centroidal_quadruped_stand_euler_v0": "centroidal_quadruped/gaits/stand_euler_v0.jld2",
+    "centroidal_quadruped_inplace_trot_v0": "centroidal_quadruped/gaits/inplace_trot_v0.jld2",
+}
+
+
+def pins():
+    for name, gait_file in PIN_GAITS.items():
+        gait = load_split_traj_alt(os.path.join(REF, gait_file))
+        np.savez_compressed(os.path.join(OUT, f"{name}_gait.npz"), **gait)
+        print("pin", name, "H =", gait["u"].shape[0], "h =", gait["h"], "mu =", gait["mu"])
+
+
 def main(robots=None):
     os.makedirs(OUT, exist_ok=True)
+    if not robots or "pins" in robots:
+        pins()
+        if robots == ["pins"]:
+            return
     if not robots or "hopper_2D" in robots:
         hopper()
     for name, (gait_file, kappa) in CONFIGS.items():

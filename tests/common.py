@@ -126,3 +126,71 @@ def independent_violation(robot, lin, knot, theta, z, alt=None):
         r_vio[i] = np.abs(r[lin_rows]).max()
         k_vio[i] = np.abs(z[i][idx.y1] * z[i][idx.y2]).max()
     return r_vio, k_vio
+
+
+# ---- the PRODUCT's generated residual code evaluated on the host (no oracle involved) ---------------------------
+GEN_DIR = os.path.join(ROOT, "contactimplicitmpc.jl_b200", "csrc", "gen")
+GEN_TAG = {"hopper_2D": "hopper2d", "quadruped": "quadruped", "flamingo": "flamingo", "centroidal_quadruped": "centroidal",
+           "quadruped_payload": "quadruped_payload", "centroidal_quadruped_payload": "centroidal_payload"}
+_GEN_SHIM = r'''
+#include "residual_%(tag)s.h"
+using namespace cimpc::gen_%(tag)s;
+extern "C" {
+int nnz() { return NNZ; }
+void pattern(int* row, int* col) { for (int k = 0; k < NNZ; ++k) { row[k] = RZ_ROW[k]; col[k] = RZ_COL[k]; } }
+void r_eval(const double* z, const double* th, double kappa, double* r) {
+  eval_r([&](int i) { return z[i]; }, [&](int i) { return th[i]; }, kappa, [&](int i, double v) { r[i] = v; });
+}
+void rz_eval(const double* z, const double* th, double* J) {
+  eval_rz([&](int i) { return z[i]; }, [&](int i) { return th[i]; }, [&](int k, double v) { J[k] = v; });
+}
+int nnzt() { return NNZT; }
+void pattern_t(int* row, int* col) { for (int k = 0; k < NNZT; ++k) { row[k] = RTH_ROW[k]; col[k] = RTH_COL[k]; } }
+void rth_eval(const double* z, const double* th, double* J) {
+  eval_rth([&](int i) { return z[i]; }, [&](int i) { return th[i]; }, [&](int k, double v) { J[k] = v; });
+}
+}
+'''
+
+
+class GeneratedResidual:
+    """`csrc/gen/residual_<tag>.h` (what the CUDA kernels compile) built for the host with g++ and called via ctypes."""
+
+    def __init__(self, robot: str, workdir: str):
+        import ctypes as C
+        import subprocess
+        tag = GEN_TAG[robot]
+        nq, nu, nw, nc, nb = SIZES[robot.replace("_payload", "")]
+        self.nz, self.nth = nq + 4 * nc + 2 * nb, 2 * nq + nu + nw + 2
+        src = os.path.join(workdir, f"shim_{tag}.cpp")
+        so = os.path.join(workdir, f"shim_{tag}.so")
+        with open(src, "w") as f:
+            f.write(_GEN_SHIM % {"tag": tag})
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", f"-I{GEN_DIR}", src, "-o", so], check=True)
+        self.lib = lib = C.CDLL(so)
+        lib.r_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+        self.nnz, self.nnzt = lib.nnz(), lib.nnzt()
+        self.row = np.zeros(self.nnz, np.int32); self.col = np.zeros(self.nnz, np.int32)
+        lib.pattern(self.row.ctypes.data_as(C.c_void_p), self.col.ctypes.data_as(C.c_void_p))
+        self.trow = np.zeros(self.nnzt, np.int32); self.tcol = np.zeros(self.nnzt, np.int32)
+        lib.pattern_t(self.trow.ctypes.data_as(C.c_void_p), self.tcol.ctypes.data_as(C.c_void_p))
+
+    def r(self, z, th, kappa):
+        z, th = np.ascontiguousarray(z, dtype=np.float64), np.ascontiguousarray(th, dtype=np.float64)
+        out = np.zeros(self.nz)
+        self.lib.r_eval(z.ctypes.data, th.ctypes.data, float(kappa), out.ctypes.data)
+        return out
+
+    def rz(self, z, th):
+        z, th = np.ascontiguousarray(z, dtype=np.float64), np.ascontiguousarray(th, dtype=np.float64)
+        J = np.zeros(self.nnz)
+        self.lib.rz_eval(z.ctypes.data, th.ctypes.data, J.ctypes.data)
+        d = np.zeros((self.nz, self.nz)); d[self.row, self.col] = J
+        return d
+
+    def rth(self, z, th):
+        z, th = np.ascontiguousarray(z, dtype=np.float64), np.ascontiguousarray(th, dtype=np.float64)
+        J = np.zeros(self.nnzt)
+        self.lib.rth_eval(z.ctypes.data, th.ctypes.data, J.ctypes.data)
+        d = np.zeros((self.nz, self.nth)); d[self.trow, self.tcol] = J
+        return d
