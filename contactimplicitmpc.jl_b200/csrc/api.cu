@@ -23,11 +23,13 @@ struct PrepParams {
   const double* rz0;   // nz × nz × H
   const double* rth0;  // nz × nθ × H
   double* lin;         // H × stride
+  int* flag;           // set to 1 when a knot lacks the block structure the reduced Schur complement relies on
 };
 
 __global__ void __launch_bounds__(128) prep_kernel(const PrepParams p) {
   const LinLayout& a = p.lay;
   const int nx = a.nx, ny = a.ny, nz = a.nz, nth = a.nth, ncol = a.ncol, G = a.group;
+  const int nr = a.nr, nrp = a.nrp, npsi = ny - nr;
   const int t = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const double* z0 = p.z0 + (size_t)t * nz;
   const double* th0 = p.th0 + (size_t)t * nth;
@@ -147,20 +149,113 @@ __global__ void __launch_bounds__(128) prep_kernel(const PrepParams p) {
     const int l = e % G, j = e / G;
     L[a.o_ca2 + 2 * e] = (l < ny) ? CAi[l + j * ny] : 0.0;
     L[a.o_ca2 + 2 * e + 1] = (l < nx) ? Ai[l + j * nx] : 0.0;
-    L[a.o_aibr + e] = (l < ny) ? AiB[j + l * nx] : 0.0;
+    L[a.o_aibr + e] = (l < nr) ? AiB[j + l * nx] : 0.0;
   }
-  for (int e = tid; e < ny * G; e += nt) {  // AIBC: AiB[l][j]; S0, S0T
+  // ---- reduced Schur complement (dims.cuh): S0 = [A0 B; C D0] over y1 = [γ1; b1 | ψ1], rows [imp; mdp | fri] ----
+  // structure the elimination of ψ1 relies on (all exact zeros of the residual, simulation.jl:133-158)
+  for (int e = tid; e < npsi * npsi; e += nt)
+    if (S0[(nr + e % npsi) + (nr + e / npsi) * ny] != 0.0) *p.flag = 1;        // D0 = Ry1[fri, ψ] = 0
+  for (int e = tid; e < nx * npsi; e += nt)
+    if (AiB[e % nx + (nr + e / nx) * nx] != 0.0) *p.flag = 1;                  // Dy1[:, ψ] = 0
+  for (int l = tid; l < nr; l += nt) {                                           // B: at most one non-zero per row
+    int cnt = 0;
+    for (int c = 0; c < npsi; ++c) cnt += (S0[l + (nr + c) * ny] != 0.0);
+    if (cnt > 1) *p.flag = 1;
+  }
+  // c(l), b0(c): contact of every reduced row and the first row of every contact (shared scratch: reuse M)
+  int* cidv = reinterpret_cast<int*>(M);  // [nr] c(l), then [npsi] b0(c)
+  int* b0v = cidv + nr;
+  __syncthreads();
+  if (tid == 0) {
+    for (int c = 0; c < npsi; ++c) b0v[c] = -1;
+    for (int l = 0; l < nr; ++l) {
+      cidv[l] = -1;
+      for (int c = 0; c < npsi; ++c)
+        if (S0[l + (nr + c) * ny] != 0.0) {
+          cidv[l] = c;
+          if (b0v[c] < 0) b0v[c] = l;
+        }
+    }
+    for (int c = 0; c < npsi; ++c)
+      if (b0v[c] < 0) *p.flag = 1;  // ψ_c must couple to at least one row
+  }
+  __syncthreads();
+  for (int e = tid; e < nrp * G; e += nt) {  // AIBC, A0 (+ identity padding), A0ᵀ, BC, BCᵀ, AB, ABᵀ
     const int l = e % G, j = e / G;
-    L[a.o_aibc + e] = (l < nx) ? AiB[l + j * nx] : 0.0;
-    L[a.o_s0 + e] = (l < ny) ? S0[l + j * ny] : 0.0;
-    L[a.o_s0t + e] = (l < ny) ? S0[j + l * ny] : 0.0;
+    L[a.o_aibc + e] = (l < nx && j < nr) ? AiB[l + j * nx] : 0.0;
+    const bool in = l < nr && j < nr;
+    const double pad = (l == j && l >= nr && l < nrp) ? 1.0 : 0.0;
+    L[a.o_s0 + e] = in ? S0[l + j * ny] : pad;
+    L[a.o_s0t + e] = in ? S0[j + l * ny] : pad;
+    double bc = 0.0, bct = 0.0, ab = 0.0, abt = 0.0;
+    if (in) {
+      const int cl = cidv[l], cj = cidv[j];
+      if (cl >= 0 && b0v[cl] >= 0) {
+        bc = S0[l + (nr + cl) * ny] * S0[(nr + cl) + j * ny];  // B[l,c]·C[c,j]
+        ab = S0[b0v[cl] + j * ny];                              // A0[b0(l), j]
+      }
+      if (cj >= 0 && b0v[cj] >= 0) {
+        bct = S0[j + (nr + cj) * ny] * S0[(nr + cj) + l * ny];
+        abt = S0[b0v[cj] + l * ny];
+      }
+    }
+    if (l >= nr && l < ny && j < nr && b0v[l - nr] >= 0) ab = S0[b0v[l - nr] + j * ny];  // ψ lanes: row b0 of their contact
+    L[a.o_bc + e] = bc;
+    L[a.o_bct + e] = bct;
+    L[a.o_ab + e] = ab;
+    L[a.o_abt + e] = abt;
   }
-  for (int e = tid; e < G; e += nt) L[a.o_ry2 + e] = (e < ny) ? Ry2[e] : 0.0;
-  for (int e = tid; e < ny * ncol; e += nt) {  // W = CAi Rθdyn − Rθrst  (first ncol columns), W[k][c] at c*ny + k
+  for (int l = tid; l < G; l += nt) {  // CRW: the (at most NFR) non-zeros of row l − nr of C = S0[fri, γb]
+    int k = 0;
+    if (l >= nr && l < ny)
+      for (int j = 0; j < nr; ++j) {
+        const double v = S0[l + j * ny];
+        if (v != 0.0) {
+          if (k < a.nfr) {
+            L[a.o_crw + (2 * k) * G + l] = v;
+            L[a.o_crw + (2 * k + 1) * G + l] = (double)j;
+          } else {
+            *p.flag = 1;
+          }
+          ++k;
+        }
+      }
+  }
+  for (int e = tid; e < G; e += nt) {  // per-lane scalars
+    L[a.o_ry2 + e] = (e < ny) ? Ry2[e] : 0.0;
+    double bv = 0.0, cid = -1.0, b0 = -1.0, rho = 0.0, pb0 = -1.0, ibv0 = 0.0;
+    if (e < nr && cidv[e] >= 0 && b0v[cidv[e]] >= 0) {
+      const int c = cidv[e];
+      bv = S0[e + (nr + c) * ny];
+      cid = (double)c;
+      b0 = (double)b0v[c];
+      rho = bv / S0[b0v[c] + (nr + c) * ny];
+      ibv0 = 1.0 / S0[b0v[c] + (nr + c) * ny];
+    }
+    if (e >= nr && e < ny && b0v[e - nr] >= 0) {
+      pb0 = (double)b0v[e - nr];
+      ibv0 = 1.0 / S0[b0v[e - nr] + e * ny];
+    }
+    L[a.o_bv + e] = bv;
+    L[a.o_cid + e] = cid;
+    L[a.o_b0 + e] = b0;
+    L[a.o_rho + e] = rho;
+    L[a.o_pb0 + e] = pb0;
+    L[a.o_ibv0 + e] = ibv0;
+  }
+  for (int j = tid; j < nrp; j += nt) {  // per-row scalars at uniform addresses
+    const bool has = j < nr && cidv[j] >= 0 && b0v[cidv[j]] >= 0;
+    L[a.o_cidu + j] = has ? (double)cidv[j] : -1.0;
+    L[a.o_rhou + j] = has ? S0[j + (nr + cidv[j]) * ny] / S0[b0v[cidv[j]] + (nr + cidv[j]) * ny] : 0.0;
+    L[a.o_b0u + j] = has ? (double)b0v[cidv[j]] : (double)j;
+  }
+  for (int e = tid; e < ny * ncol; e += nt) {  // W = CAi Rθdyn − Rθrst (first ncol columns, rows γ1 b1), W[k][c] at c*NRP + k
     const int i = e % ny, j = e / ny;
     double s = 0.0;
     for (int k = 0; k < nx; ++k) s = fma(CAi[i + k * ny], Rtd[k + j * nx], s);
-    L[a.o_w + e] = s - Rtr[e];
+    s -= Rtr[i + j * ny];
+    if (i < nr) L[a.o_w + j * nrp + i] = s;
+    else if (s != 0.0) *p.flag = 1;  // the fri rows do not depend on (q0, q1, u1)
   }
   for (int e = tid; e < ncol * G; e += nt) {  // AR = Ai Rθdyn[:, 1:ncol], AR[l][c] at c*G + l
     const int l = e % G, j = e / G;
@@ -231,6 +326,8 @@ struct cimpc_ctx {
   size_t sim_scratch_doubles = 0;
   double* dense = nullptr;  // dense linearization arrays of the current reference (see alloc_dense)
   int32_t dense_h = 0;
+  bool lin_bad_structure = false;
+  int* prep_flag = nullptr;  // device int written by prep_kernel (structure check of the uploaded linearization)
 };
 
 static int cuda_fail(cimpc_ctx* c, cudaError_t e, const char* where) {
@@ -336,6 +433,7 @@ int cimpc_destroy(cimpc_ctx* ctx) {
   if (ctx->nw.arena) cudaFree(ctx->nw.arena);
   if (ctx->sim_scratch) cudaFree(ctx->sim_scratch);
   if (ctx->dense) cudaFree(ctx->dense);
+  if (ctx->prep_flag) cudaFree(ctx->prep_flag);
   if (ctx->nw.h_active) cudaFreeHost(ctx->nw.h_active);
   if (ctx->dev) cudaFree(ctx->dev);
   if (ctx->pin) cudaFreeHost(ctx->pin);
@@ -386,7 +484,13 @@ static cudaError_t run_prep(cimpc_ctx* ctx, int32_t H, cudaStream_t s) {
     if (e != cudaSuccess) return e;
   }
   const DensePtrs d = dense_ptrs(ctx);
-  PrepParams pp{l, d.z0, d.t0, d.r0, d.rz, d.rt, ctx->lin};
+  if (!ctx->prep_flag) {
+    e = cudaMalloc(&ctx->prep_flag, sizeof(int));
+    if (e != cudaSuccess) return e;
+  }
+  e = cudaMemsetAsync(ctx->prep_flag, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  PrepParams pp{l, d.z0, d.t0, d.r0, d.rz, d.rt, ctx->lin, ctx->prep_flag};
   const size_t smem = sizeof(double) * ((size_t)4 * l.nx * l.nx + 4 * l.nx * l.ny + 2 * l.ny * l.ny + l.ny +
                                         (size_t)(l.nx + l.ny) * l.nth + 16);
   if (smem > 48 * 1024) {
@@ -396,8 +500,13 @@ static cudaError_t run_prep(cimpc_ctx* ctx, int32_t H, cudaStream_t s) {
   prep_kernel<<<H, 128, smem, s>>>(pp);
   ctx->launches++;
   e = cudaGetLastError();
+  int flag = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, ctx->prep_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e == cudaSuccess) ctx->h_ref = H;
+  if (e == cudaSuccess) {
+    ctx->h_ref = flag ? 0 : H;  // a linearization without the contact structure is not usable
+    ctx->lin_bad_structure = flag != 0;
+  }
   return e;
 }
 
@@ -417,6 +526,7 @@ int cimpc_upload_linearization(cimpc_ctx* ctx, int32_t H, const double* z0, cons
   CK(cudaMemcpyAsync(d.rt, rth0, nz * nth * H * 8, cudaMemcpyHostToDevice, s));
   cudaError_t e = run_prep(ctx, H, s);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "cimpc_upload_linearization");
+  if (ctx->lin_bad_structure) return CIMPC_ERR_UNSUPPORTED_MODEL;
   return CIMPC_OK;
 }
 
@@ -437,6 +547,7 @@ int cimpc_linearize(cimpc_ctx* ctx, int32_t H, const double* z0, const double* t
   ctx->launches++;
   e = run_prep(ctx, H, s);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "cimpc_linearize");
+  if (ctx->lin_bad_structure) return CIMPC_ERR_UNSUPPORTED_MODEL;
   return CIMPC_OK;
 }
 

@@ -30,7 +30,27 @@ struct Dims {
   static constexpr int G = imax(4, pow2_ceil(imax(NX, NY)));
   static_assert(G <= 32, "subproblem rows must fit one warp");
   static_assert(NX <= NY, "row padding below assumes nx <= ny");
-  static_assert(NY % 4 == 0, "Gauss-Jordan block size");
+
+  // ---- reduced Schur complement -----------------------------------------------------------------
+  // In S = Ry1 − diag(Ry2 ŷ2/ŷ1) − Rx Dx⁻¹ Dy1 the friction-cone rows `fri` (s2 − (μγ1 − E b1)) do not depend on q2
+  // and the ψ1 columns do not enter the dynamics (src/simulation/simulation.jl:133-158: Rx[fri,:] = 0, Dy1[:,ψ] = 0,
+  // Ry1[fri,ψ] = 0), so with y1 = [γ1; b1 | ψ1], rst = [imp; mdp | fri]
+  //     S = [ A  B ]     A (NR×NR) iterate-dependent only on its diagonal,  B = Ry1[imp∪mdp, ψ] (= [0; −Eᵀ]) constant,
+  //         [ C  D ]     C = Ry1[fri, γb] (= [−μI  E]) constant,            D = −diag(w_ψ),  w = Ry2 ŷ2/ŷ1,
+  // and t_ψ is eliminated in closed form before the dense inversion (NR = nc + nb rows: 16 → 12 for the quadruped,
+  // 24 → 20 centroidal).  Column ψ_c of S holds −w_ψ,c (row fri_c) and the entries B[l, c] of the rows l of contact c
+  // (one non-zero per row); partial pivoting on that column picks the larger of the two, PER CONTACT AND ITERATE:
+  //   w_ψ,c ≥ |B| ("D pivot", sticking contact):  row l ← A[l,:] + (B[l,c]/w_ψ,c) C[c,:],   t_ψ = (C t_r − r_ψ)/w_ψ
+  //   w_ψ,c < |B| ("B pivot", sliding / open contact; b0 = first row of contact c, ρ_l = B[l,c]/B[b0,c]):
+  //        row b0 ← C[c,:] + (w_ψ,c/B[b0,c]) A[b0,:],   row l ≠ b0 ← A[l,:] − ρ_l A[b0,:],   t_ψ = (r_b0 − A[b0,:] t_r)/B[b0,c]
+  // so every multiplier is ≤ 1 — eliminating with 1/w_ψ alone loses cond ≈ 1/w_ψ digits on sliding contacts (measured:
+  // 1e-5 instead of 1e-13 on one of 40 960 benchmark problems).  Every row is a combination of three CONSTANT rows
+  // (A0[l,:], BC[l,:] = B[l,c]·C[c,:], AB[l,:] = A0[b0,:]) with three scalars, plus its diagonal terms.
+  static constexpr int NPSI = NC;                                 // eliminated pairs (ψ1, s2)
+  static constexpr int NR = NY - NPSI;                            // rows of the dense block that is inverted
+  static constexpr int NRP = round_up(NR, 4);                     // padded with identity rows (Gauss-Jordan block of 4)
+  static constexpr int NFR = 1 + NB / NC;                         // non-zeros of a row of C: γ_c and the b's of contact c
+  static_assert(NRP <= G, "reduced rows must fit the lane group");
 
   // ---- LinStore: per-knot constants, fp64, offsets in doubles --------------------------------
   // Every lane-indexed matrix is padded to G rows and stored "lane fastest" so that the G lanes of a
@@ -40,13 +60,30 @@ struct Dims {
   // Shared-memory part (copied per CTA by one cp.async.bulk when the knot changes):
   static constexpr int O_RES = 0;                         // (NX+NY)×G×2  {[Dx Dy1][l][j], [Rx Ry1][l][j]}
   static constexpr int O_CA2 = O_RES + (NX + NY) * G * 2;  // NX×G×2       {CAi[l][j], Ai[l][j]}
-  static constexpr int O_AIBC = O_CA2 + NX * G * 2;        // NY×G         AiB[l][j] at j*G + l
-  static constexpr int O_AIBR = O_AIBC + NY * G;           // NX×G         AiB[i][l] at i*G + l
-  static constexpr int O_S0 = O_AIBR + NX * G;             // NY×G         S0[l][j]  at j*G + l
-  static constexpr int O_S0T = O_S0 + NY * G;              // NY×G         S0[j][l]  at j*G + l
-  static constexpr int O_RY2 = O_S0T + NY * G;             // G            Ry2[l]
-  static constexpr int O_W = O_RY2 + G;                    // NCOL×NY      W[k][c]   at c*NY + k   (uniform reads)
-  static constexpr int O_AR = O_W + NCOL * NY;             // NCOL×G       AR[l][c]  at c*G + l
+  static constexpr int O_AIBC = O_CA2 + NX * G * 2;        // NRP×G        AiB[l][j] at j*G + l   (ψ columns are zero)
+  static constexpr int O_AIBR = O_AIBC + NRP * G;          // NX×G         AiB[i][l] at i*G + l
+  static constexpr int O_S0 = O_AIBR + NX * G;             // NRP×G        A0[l][j]  at j*G + l   (identity padding)
+  static constexpr int O_S0T = O_S0 + NRP * G;             // NRP×G        A0[j][l]  at j*G + l
+  static constexpr int O_BC = O_S0T + NRP * G;             // NRP×G        BC[l][j]  at j*G + l
+  static constexpr int O_BCT = O_BC + NRP * G;             // NRP×G        BC[j][l]  at j*G + l
+  static constexpr int O_AB = O_BCT + NRP * G;             // NRP×G        AB[l][j] = A0[b0(l)][j] at j*G + l
+  static constexpr int O_ABT = O_AB + NRP * G;             // NRP×G        AB[j][l]  at j*G + l
+  static constexpr int O_CRW = O_ABT + NRP * G;            // NFR×G×2      k-th non-zero of row l−NR of C: {value, column} (ψ lanes)
+  // per-lane scalars (G each): Ry2[l]; B[l,c(l)]; c(l) (−1: none); lane of b0(c(l)) (−1: none); ρ_l;
+  // 1/B[b0,c] of the lane's contact; ψ lanes: lane of b0(c)
+  static constexpr int O_RY2 = O_CRW + NFR * G * 2;
+  static constexpr int O_BV = O_RY2 + G;
+  static constexpr int O_CID = O_BV + G;
+  static constexpr int O_B0 = O_CID + G;
+  static constexpr int O_RHO = O_B0 + G;
+  static constexpr int O_PB0 = O_RHO + G;
+  static constexpr int O_IBV0 = O_PB0 + G;
+  // per-row scalars read at uniform addresses (transposed build, transformed sensitivity right-hand sides)
+  static constexpr int O_CIDU = O_IBV0 + G;                // NRP
+  static constexpr int O_RHOU = O_CIDU + NRP;              // NRP
+  static constexpr int O_B0U = O_RHOU + NRP;               // NRP          b0(c(j)), j itself for rows without ψ coupling
+  static constexpr int O_W = O_B0U + NRP;                   // NCOL×NRP     W[k][c]   at c*NRP + k   (uniform reads)
+  static constexpr int O_AR = O_W + NCOL * NRP;            // NCOL×G       AR[l][c]  at c*G + l
   static constexpr int SMEM_DOUBLES = round_up(O_AR + NCOL * G, 2);
   // Global-only part (touched once per subproblem, in the prologue; served by L1/L2):
   static constexpr int O_C0 = SMEM_DOUBLES;                // G×2          {cdyn0[l], crst0[l]}

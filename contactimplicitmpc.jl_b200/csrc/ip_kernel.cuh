@@ -57,6 +57,10 @@ struct IpParams {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int UNPIV = 1 << 20;
+// Elimination of ψ1 (dims.cuh): the D pivot (−w_ψ) is kept while w_ψ ≥ PSI_PIVOT_RATIO·|B|; 1 = partial pivoting on the
+// ψ column (every multiplier ≤ 1).  Measured with 1e-3 (multipliers up to 1e3): agreement with the LU oracle unchanged at
+// κ_tol ≥ 1e-5, but iteration counts at κ_tol = 1e-8 start to depend on 1e-13 perturbations of the linearization.
+constexpr double PSI_PIVOT_RATIO = 1.0;
 
 // Guaranteed compile-time unrolling (register arrays must never be indexed dynamically).
 template <int B, int... Is, class F>
@@ -121,19 +125,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // Per-group shared-memory scratch (doubles).
 template <class D>
 struct GroupScratch {
-  static constexpr int NX = D::NX, NY = D::NY;
+  static constexpr int NX = D::NX, NY = D::NY, NRP = D::NRP;
   static constexpr int XYN = round_up(imax(NX + NY, D::NTH), 2);
   static constexpr int O_XY = 0;                 // [x; y1] exchange (θ in the prologue, rdyn for the products)
   static constexpr int O_WV = O_XY + XYN;        // RHS of a solve, permuted to pivot order
-  static constexpr int O_TV = O_WV + NY;         // solution of a solve, natural order
-  static constexpr int O_PROW = O_TV + NY;       // pivot row of a Gauss-Jordan step, double-buffered by step parity
-  static constexpr int O_SENS = O_PROW + 2 * NY; // sensitivity workspace
-  static constexpr int LDP = NY + 1;             // padded leading dimension of lane-major scratch matrices
-  static constexpr int O_AIBP = O_SENS;          // NX×NY   AiB with columns permuted to pivot order
-  static constexpr int A_SZ = imax(NX * NY, D::MODE ? NY * LDP : 0);  // AiBp, later aliased by S⁻¹ rows
-  static constexpr int O_P1 = O_SENS + round_up(A_SZ, 2);    // NX×LDP  P1 = AiB S⁻¹
-  static constexpr int O_PL = O_P1 + round_up(NX * LDP, 2);  // NY ints: pivot lane of each step
-  static constexpr int DOUBLES = round_up(O_PL + (NY + 1) / 2, 2);
+  static constexpr int O_TV = O_WV + NRP;        // solution of a solve, natural order
+  static constexpr int O_PROW = O_TV + NRP;      // pivot row of a Gauss-Jordan step, double-buffered by step parity
+  static constexpr int O_V = O_PROW + 2 * NRP;   // {1/w_ψ,c, w_ψ,c} of the eliminated pairs
+  static constexpr int O_G = O_V + 2 * D::NPSI;  // rhs_ψ,c of the solve in flight
+  static constexpr int O_VR = O_G + round_up(D::NPSI, 2);  // {a1_j, a2_j, a3_j, ·} per ROW j (transposed load)
+  static constexpr int O_SENS = O_VR + 4 * NRP;  // sensitivity workspace
+  static constexpr int LDP = NRP + 1;            // padded leading dimension of lane-major scratch matrices
+  static constexpr int O_AIBP = O_SENS;          // NX×NRP   AiB with columns permuted to pivot order
+  static constexpr int A_SZ = imax(NX * NRP, D::MODE ? NRP * LDP : 0);  // AiBp, later aliased by S_red⁻¹ rows
+  static constexpr int O_P1 = O_SENS + round_up(A_SZ, 2);    // NX×LDP  P1 = AiB S_red⁻¹
+  static constexpr int O_PL = O_P1 + round_up(NX * LDP, 2);  // NRP ints: pivot lane of each step
+  static constexpr int DOUBLES = round_up(O_PL + (NRP + 1) / 2, 2);
 };
 
 template <class D>
@@ -141,7 +148,15 @@ struct Ctx {  // per-lane registers of one subproblem
   double x, y1, y2;
   double cdyn, crst, ry2;
   double rdyn, rrst, rbil;
-  double M[D::NY];  // row of P·S⁻¹ in pivot-order column slots, WITHOUT its pivot scaling (see invert)
+  // elimination of ψ1 (dims.cuh): constants of this lane's row, and the pivot choice of the current iterate
+  double bv;        // B[l, c(l)]: coupling of reduced row l to its eliminated ψ (0: none)
+  int cid;          // c(l), −1: none
+  int b0;           // lane of the first row of contact c(l) (reduced lanes) / of contact l − NR (ψ lanes); −1: none
+  double wl;        // w_l = Ry2 ŷ2 / ŷ1 of this lane's pair at the current iterate
+  double a1, a2, a3;  // row l of S_red = a1·A[l,:] + a2·BC[l,:] + a3·A[b0,:]   (a2 doubles as v_ψ = 1/w_ψ on ψ lanes)
+  bool dpiv;        // this lane's contact is eliminated with the D pivot
+  bool any_b;       // group-uniform: some contact of this subproblem uses the B pivot
+  double M[D::NRP]; // row of P·S_red⁻¹ in pivot-order column slots, WITHOUT its pivot scaling (see invert)
   double msc;       // 1 / pivot of this lane's row: the row of the inverse is msc · M[]
   int mystep;       // Gauss-Jordan step at which this lane's row was the pivot row
 };
@@ -196,7 +211,7 @@ __device__ __forceinline__ void residual(const double* __restrict__ Ls, double* 
 // slower (58.2 vs 59.9 M subproblems/s).
 template <class D, bool RECORD_PL>
 __device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l, int gshift, bool hy) {
-  constexpr int NY = D::NY, G = D::G;
+  constexpr int NY = D::NRP, G = D::G;  // the reduced block (dims.cuh); `hy` = lane owns one of its rows
   using S = GroupScratch<D>;
   c.mystep = UNPIV;
   c.msc = 0.0;
@@ -271,8 +286,9 @@ __device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l
 // t = S⁻¹ w with the inverse held as c.M: w is scattered to pivot order, every lane forms its dot
 // product, the result is scattered back to natural order.  Returns t_l; sc[O_TV + j] = t_j for all j.
 template <class D>
-__device__ __forceinline__ double apply_inverse(const Ctx<D>& c, double* __restrict__ sc, int l, bool hy, double w) {
-  constexpr int NY = D::NY;
+__device__ __forceinline__ double apply_inverse(const Ctx<D>& c, double* __restrict__ sc, int l, bool hy, double w,
+                                                double& raw) {
+  constexpr int NY = D::NRP;
   using S = GroupScratch<D>;
   if (hy) sc[S::O_WV + c.mystep] = w;
   __syncwarp();
@@ -285,7 +301,8 @@ __device__ __forceinline__ double apply_inverse(const Ctx<D>& c, double* __restr
     a2 = fma(c.M[4 * j + 2], w.x, a2);
     a3 = fma(c.M[4 * j + 3], w.y, a3);
   });
-  a0 = ((a0 + a1) + (a2 + a3)) * c.msc;
+  raw = (a0 + a1) + (a2 + a3);  // lanes outside the block: product of their passenger row (load_schur) with the RHS
+  a0 = raw * c.msc;
   if (hy) sc[S::O_TV + c.mystep] = a0;
   __syncwarp();
   return hy ? sc[S::O_TV + l] : 0.0;
@@ -300,18 +317,156 @@ __device__ __forceinline__ double step_length(bool hy, double y1, double y2, dou
   return gmin<D::G>(a);
 }
 
-// rzlin!: row l of S (or of Sᵀ) = S0 − diag(Ry2 ŷ2 / ŷ1).
+// rzlin!: row l of S_red (or of S_redᵀ), the Schur complement with ψ1 eliminated (dims.cuh):
+//   row l = a1·(A0[l,:] − w_l e_l) + a2·BC[l,:] + a3·(A0[b0,:] − w_b0 e_b0)
+// with (a1, a2, a3) = (1, 0, 0) rows without ψ coupling; (1, 1/w_ψ, 0) D pivot; (w_ψ/B_l, 1/B_l, 0) B pivot, l = b0;
+// (1, 0, −ρ_l) B pivot, l ≠ b0.  Only one of a2, a3 is non-zero, so the row is built from TWO constant rows in one
+// pass for every case: a1·A0[l,:] + ax·aux[l,:], aux = BC or AB selected per lane.
+// The ψ lanes (which own no row of the block) load A[b0,:] of their contact as PASSENGER rows: they are never pivots, the
+// Gauss-Jordan updates turn them into −A[b0,:] S_red⁻¹, and apply_inverse then hands them −A[b0,:] t_r — the t_ψ of the
+// B pivot — at no extra instruction.
 template <class D, bool TRANSPOSED>
-__device__ __forceinline__ void load_schur(Ctx<D>& c, const double* __restrict__ Ls, int l, bool hy, double reg) {
-  constexpr int NY = D::NY, G = D::G;
+__device__ __forceinline__ void load_schur(Ctx<D>& c, const double* __restrict__ Ls, double* __restrict__ sc, int l,
+                                           int gshift, bool hy, double reg) {
+  constexpr int NR = D::NR, NRP = D::NRP, G = D::G;
+  using S = GroupScratch<D>;
+  const bool hr = l < NR, hm = l < NRP, hp = hy && l >= NR;
   const double y1r = fmax(c.y1, reg), y2r = fmax(c.y2, reg);
-  const double dd = c.ry2 * y2r / y1r;
-  const double* S0 = Ls + (TRANSPOSED ? D::O_S0T : D::O_S0) + l;
-  static_for<0, NY>([&](auto J) {
-    constexpr int j = decltype(J)::value;
-    const double s0 = S0[j * G];
-    c.M[j] = hy ? ((j == l) ? s0 - dd : s0) : 0.0;
-  });
+  c.wl = hy ? c.ry2 * y2r / y1r : 1.0;
+  if (hp) *reinterpret_cast<double2*>(sc + S::O_V + 2 * (l - NR)) = make_double2(1.0 / c.wl, c.wl);
+  __syncwarp();
+  c.a1 = 1.0; c.a2 = 0.0; c.a3 = 0.0;
+  c.dpiv = true;
+  if (hr && c.cid >= 0) {
+    const double2 vw = lds2(sc + S::O_V + 2 * c.cid);  // {1/w_ψ, w_ψ}
+    c.dpiv = vw.y * fabs(Ls[D::O_IBV0 + l]) >= PSI_PIVOT_RATIO;  // same expression on the ψ lane
+    if (c.dpiv) {
+      c.a2 = vw.x;
+    } else if (l == c.b0) {
+      c.a2 = 1.0 / c.bv;
+      c.a1 = vw.y * c.a2;
+    } else {
+      c.a3 = -Ls[D::O_RHO + l];
+    }
+  }
+  if (hp) {  // ψ lanes: pivot choice of their own contact, a2 = 1/w_ψ
+    c.dpiv = c.wl * fabs(Ls[D::O_IBV0 + l]) >= PSI_PIVOT_RATIO;
+    c.a2 = 1.0 / c.wl;
+  }
+  {  // does THIS subproblem have a contact on its B pivot (group-uniform)
+    const unsigned bal = __ballot_sync(FULL, !c.dpiv);
+    c.any_b = ((G == 32) ? bal : ((bal >> gshift) & ((1u << (G & 31)) - 1u))) != 0u;
+  }
+  // w of the first row of this lane's contact (own value on lanes without one)
+  const double wb0 = __shfl_sync(FULL, c.wl, gshift + (c.b0 >= 0 ? c.b0 : l));
+  if constexpr (!TRANSPOSED) {
+    const bool use_ab = (hr && c.a3 != 0.0) || (hp && NRP == NR);     // rows l ≠ b0 of a B-pivot contact; passengers
+    const double a1 = hr ? c.a1 : ((hm && NRP != NR) ? 1.0 : 0.0);      // padding rows keep their identity row of A0
+    const double ax = hr ? (c.a3 != 0.0 ? c.a3 : c.a2) : ((hp && NRP == NR) ? 1.0 : 0.0);
+    const double* A0 = Ls + D::O_S0 + l;
+    const double* AX = Ls + (use_ab ? D::O_AB : D::O_BC) + l;
+    const int jb = use_ab ? c.b0 : -1;
+    const double dl = hr ? a1 * c.wl : 0.0, db = ax * wb0;
+    static_for<0, NRP>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      double m = fma(a1, A0[j * G], ax * AX[j * G]);
+      if (j == l) m -= dl;
+      if (j == jb) m -= db;
+      c.M[j] = m;
+    });
+  } else {
+    if (hm) {
+      *reinterpret_cast<double2*>(sc + S::O_VR + 4 * l) = make_double2(hr ? c.a1 : 1.0, hr ? c.a2 : 0.0);
+      sc[S::O_VR + 4 * l + 2] = hr ? c.a3 : 0.0;
+    }
+    __syncwarp();
+    const double* A0 = Ls + D::O_S0T + l;
+    const double* BC = Ls + D::O_BCT + l;
+    const double* AB = Ls + D::O_ABT + l;
+    // column l of S_red: element j comes from row j
+    const bool is_b0_bpiv = hr && c.cid >= 0 && !c.dpiv && l == c.b0;
+    static_for<0, NRP>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      const double2 a12 = lds2(sc + S::O_VR + 4 * j);
+      const double a3 = sc[S::O_VR + 4 * j + 2];
+      double m = a12.x * A0[j * G];
+      m = fma(a12.y, BC[j * G], m);
+      m = fma(a3, AB[j * G], m);
+      if (j == l && hr) m = fma(-c.a1, c.wl, m);  // own diagonal: row l = column l
+      // rows j ≠ b0 of a B-pivot contact carry −a3_j·w_b0 in column b0: this lane IS b0, so w_b0 = w_l
+      if (is_b0_bpiv && j != l && (int)Ls[D::O_CIDU + j] == c.cid) m = fma(Ls[D::O_RHOU + j], c.wl, m);
+      c.M[j] = hm ? m : 0.0;
+    });
+  }
+}
+
+// t = S⁻¹ rhs for the full ny-vector rhs (lane l holds rhs_l) through the reduced inverse held in c.M:
+//   rhs_red,l = a1·rhs_l + a2·B_l·rhs_ψ + a3·rhs_b0,   t_r = S_red⁻¹ rhs_red,
+//   t_ψ = (C t_r − rhs_ψ)/w_ψ (D pivot)   or   (rhs_b0 − A[b0,:] t_r)/B[b0,c] (B pivot).
+// Returns t_l; sc[O_TV + j] = t_j for the reduced rows j.
+template <class D>
+__device__ __forceinline__ double schur_solve(const Ctx<D>& c, const double* __restrict__ Ls, double* __restrict__ sc,
+                                              int l, int gshift, bool hy, double rhs) {
+  constexpr int NR = D::NR, NRP = D::NRP, G = D::G;
+  using S = GroupScratch<D>;
+  const bool hr = l < NR, hm = l < NRP, hp = hy && l >= NR;
+  if (hp) sc[S::O_G + l - NR] = rhs;
+  __syncwarp();
+  const double rb0 = __shfl_sync(FULL, rhs, gshift + (c.b0 >= 0 ? c.b0 : l));  // rhs of the contact's first row
+  double rr = 0.0;
+  if (hr) {
+    rr = c.a1 * rhs;
+    if (c.cid >= 0) rr = (c.a3 != 0.0) ? fma(c.a3, rb0, rr) : fma(c.a2 * c.bv, sc[S::O_G + c.cid], rr);
+  }
+  double raw;
+  const double tr = apply_inverse<D>(c, sc, l, hm, rr, raw);
+  double tpsi_b;  // B pivot: t_ψ = (rhs_b0 − A[b0,:] t_r) / B[b0,c]
+  if constexpr (NRP == NR) {
+    tpsi_b = (rb0 + raw) * Ls[D::O_IBV0 + l];  // raw = −A[b0,:] t_r on the ψ lanes (passenger rows)
+  } else {
+    // (hopper sizes: the ψ lane doubles as the identity padding row of the block, so the product is formed explicitly)
+    double e0 = hr ? fma(c.wl, tr, rhs) : 0.0, e1 = 0.0;
+    const double* A0 = Ls + D::O_S0 + l;
+#pragma unroll
+    for (int j = 0; j < NRP; j += 2) {
+      const double2 tv = lds2(sc + S::O_TV + j);
+      e0 = fma(-A0[j * G], tv.x, e0);
+      e1 = fma(-A0[(j + 1) * G], tv.y, e1);
+    }
+    tpsi_b = __shfl_sync(FULL, e0 + e1, gshift + (c.b0 >= 0 ? c.b0 : l)) * Ls[D::O_IBV0 + l];
+  }
+  double a = -rhs;
+#pragma unroll
+  for (int k = 0; k < D::NFR; ++k) {
+    const double cv = Ls[D::O_CRW + (2 * k) * G + l];
+    const int cj = (int)Ls[D::O_CRW + (2 * k + 1) * G + l];
+    a = fma(cv, sc[S::O_TV + cj], a);
+  }
+  const double tpsi = c.dpiv ? c.a2 * a : tpsi_b;
+  return hr ? tr : (hp ? tpsi : 0.0);
+}
+
+// A contact on its B pivot has its rows of the reduced system COMBINED (load_schur): S_red t_r = T·rhs with
+// T = diag(a1) + Σ_k a3_k e_k e_b0(k)ᵀ.  For the sensitivities the right-hand sides are the constant W, so T is folded into
+// the row vectors that multiply W instead:  row ← row·T  (own row of this lane in shared memory, in place: slot b0 is
+// the only target of additions and the rows k with a3_k ≠ 0 have a1_k = 1).  Identity for D-pivot contacts.
+template <class D>
+__device__ __forceinline__ void fold_row_combination(const double* __restrict__ Ls, const double* __restrict__ sc,
+                                                     double* __restrict__ row) {
+  using S = GroupScratch<D>;
+#pragma unroll 1
+  for (int k = 0; k < D::NRP; ++k) {
+    const double a1 = sc[S::O_VR + 4 * k];
+    if (a1 != 1.0) row[k] *= a1;
+  }
+#pragma unroll 1
+  for (int k = 0; k < D::NRP; ++k) {
+    const double a3 = sc[S::O_VR + 4 * k + 2];
+    if (a3 != 0.0) {
+      const int b0 = (int)Ls[D::O_B0U + k];
+      row[b0] = fma(a3, row[k], row[b0]);
+    }
+  }
 }
 
 // differentiate_solution! restricted to the rows / columns Newton consumes:
@@ -324,17 +479,21 @@ template <class D>
 __device__ __forceinline__ void sensitivities(Ctx<D>& c, const double* __restrict__ Ls, double* __restrict__ sc, int l,
                                               int gshift, bool hx, bool hy, double reg, double* __restrict__ dzo,
                                               bool valid) {
-  constexpr int NX = D::NX, NY = D::NY, G = D::G, NCOL = D::NCOL, ND = D::ND, NYD = D::NYD;
+  // Only the reduced rows enter: AiB[:, ψ] = 0 and W[ψ, (q0, q1, u1)] = 0 (checked by prep_kernel), so
+  // δx = −(AR + AiB_r S_red⁻¹ W_r) and δ[γ1; b1] = S_red⁻¹ W_r need neither t_ψ nor the ψ rows of W.
+  constexpr int NX = D::NX, NY = D::NRP, G = D::G, NCOL = D::NCOL, ND = D::ND, NYD = D::NYD;
+  static_assert(NYD == 0 || NYD == D::NR, "force rows = reduced rows");
   using S = GroupScratch<D>;
-  load_schur<D, true>(c, Ls, l, hy, reg);
-  invert<D, (NYD > 0)>(c, sc, l, gshift, hy);  // c.M[j] = S⁻¹[q_j][k],  k = c.mystep, lane = q_k
+  const bool hm = l < NY;
+  load_schur<D, true>(c, Ls, sc, l, gshift, hy, reg);
+  invert<D, (NYD > 0)>(c, sc, l, gshift, hm);  // c.M[j] = S_red⁻¹[q_j][k],  k = c.mystep, lane = q_k
   // AiBp[i][m] = AiB[i][q_m]: lane l = q_m owns column l of AiB
-  if (hy) {
+  if (hm) {
 #pragma unroll 1
     for (int i = 0; i < NX; ++i) sc[S::O_AIBP + i * NY + c.mystep] = Ls[D::O_AIBR + i * G + l];
   }
   __syncwarp();
-  // P1[i][k] = Σ_m AiBp[i][m] · S⁻¹[q_m][k]
+  // P1[i][k] = Σ_m AiBp[i][m] · S_red⁻¹[q_m][k]
 #pragma unroll 1
   for (int i = 0; i < NX; ++i) {
     double a0 = 0.0, a1 = 0.0;
@@ -344,26 +503,28 @@ __device__ __forceinline__ void sensitivities(Ctx<D>& c, const double* __restric
       a0 = fma(c.M[2 * j], v.x, a0);
       a1 = fma(c.M[2 * j + 1], v.y, a1);
     });
-    if (hy) sc[S::O_P1 + i * S::LDP + c.mystep] = (a0 + a1) * c.msc;
+    if (hm) sc[S::O_P1 + i * S::LDP + c.mystep] = (a0 + a1) * c.msc;
   }
   __syncwarp();
   double Ar[NYD > 0 ? NY : 1];
   if constexpr (NYD > 0) {
-    // rows of S⁻¹ for the force rows: Ainv[r][k] = S⁻¹[r][k], scattered from the column-held inverse
+    // rows of S_red⁻¹ for the force rows: Ainv[r][k] = S_red⁻¹[r][k], scattered from the column-held inverse
     const int* pl = reinterpret_cast<const int*>(sc + S::O_PL);
-    if (hy) {
+    if (hm) {
       static_for<0, NY>([&](auto J) {
         constexpr int j = decltype(J)::value;
         sc[S::O_AIBP + pl[j] * S::LDP + c.mystep] = c.M[j] * c.msc;
       });
     }
     __syncwarp();
+    if (c.any_b && l < NYD) fold_row_combination<D>(Ls, sc, sc + S::O_AIBP + l * S::LDP);
     static_for<0, NY>([&](auto J) {
       constexpr int j = decltype(J)::value;
       Ar[j] = (l < NYD) ? sc[S::O_AIBP + l * S::LDP + j] : 0.0;
     });
   }
   // row l of P1 (c.M is dead: reuse its registers)
+  if (c.any_b && hx) fold_row_combination<D>(Ls, sc, sc + S::O_P1 + l * S::LDP);
   static_for<0, NY>([&](auto J) {
     constexpr int j = decltype(J)::value;
     c.M[j] = hx ? sc[S::O_P1 + l * S::LDP + j] : 0.0;
@@ -528,6 +689,9 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
       }
       __syncwarp();
       c.ry2 = Ls[D::O_RY2 + l];
+      c.bv = Ls[D::O_BV + l];
+      c.cid = (int)Ls[D::O_CID + l];
+      c.b0 = (l < D::NR) ? (int)Ls[D::O_B0 + l] : (int)Ls[D::O_PB0 + l];
       // cold start: z = 1, z[q2] = q2_init  (z_initialize!)
       c.x = hx ? p.q2_init[pi * NX + l] : 0.0;
       c.y1 = 1.0;
@@ -549,8 +713,8 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
         const double reg_it = (k_vio < o.kappa_reg) ? k_vio * o.gamma_reg : 0.0;
         const double y1r = fmax(c.y1, reg_it), y2r = fmax(c.y2, reg_it);
         // rzlin! + schur_factorize!  →  S⁻¹
-        load_schur<D, false>(c, Ls, l, hy, reg_it);
-        invert<D, false>(c, sc, l, gshift, hy);
+        load_schur<D, false>(c, Ls, sc, l, gshift, hy, reg_it);
+        invert<D, false>(c, sc, l, gshift, l < D::NRP);
 
         // constant products with u = rdyn (shared by predictor and corrector): cu = CAi u, au = Ai u
         double cu = 0.0, au = 0.0;
@@ -571,7 +735,7 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
         // ---- predictor (affine) direction: only Δy1, Δy2 are needed ----
         // (the five divisions by ŷ1 of one iteration share one correctly-rounded reciprocal)
         const double iy1 = __drcp_rn(y1r);
-        double t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * c.rbil * iy1) : 0.0);
+        double t = schur_solve<D>(c, Ls, sc, l, gshift, hy, hy ? cu - (c.rrst - c.ry2 * c.rbil * iy1) : 0.0);
         const double dy1a = -t;
         const double dy2a = hy ? (c.rbil - y2r * dy1a) * iy1 : 0.0;
         const double a_aff = step_length<D>(hy, c.y1, c.y2, dy1a, dy2a, 1.0);
@@ -583,14 +747,14 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
 
         // ---- corrector: rbil = y1∘y2 − κ + Δy1aff∘Δy2aff ----
         const double rbc = hy ? fma(c.y1, c.y2, -kap) + dy1a * dy2a : 0.0;
-        t = apply_inverse<D>(c, sc, l, hy, hy ? cu - (c.rrst - c.ry2 * rbc * iy1) : 0.0);
+        t = schur_solve<D>(c, Ls, sc, l, gshift, hy, hy ? cu - (c.rrst - c.ry2 * rbc * iy1) : 0.0);
         const double dy1 = -t;
         const double dy2 = hy ? (rbc - y2r * dy1) * iy1 : 0.0;
         double dx = au;
         {
           const double* AB = Ls + D::O_AIBC + l;
 #pragma unroll 2
-          for (int j = 0; j < NY; j += 2) {
+          for (int j = 0; j < D::NRP; j += 2) {  // AiB[:, ψ] = 0: the reduced part of t is all Δx needs
             const double2 tv = lds2(sc + S::O_TV + j);
             dx = fma(AB[j * G], tv.x, dx);
             dx = fma(AB[(j + 1) * G], tv.y, dx);

@@ -13,8 +13,9 @@
 namespace cimpc {
 
 struct LinLayout {  // runtime copy of Dims<...> (offsets in doubles)
-  int nx, ny, nz, nth, ncol, nd, group;
-  int o_res, o_ca2, o_aibc, o_aibr, o_s0, o_s0t, o_ry2, o_w, o_ar, o_c0, o_rth;
+  int nx, ny, nz, nth, ncol, nd, group, nr, nrp, nfr;
+  int o_res, o_ca2, o_aibc, o_aibr, o_s0, o_s0t, o_bc, o_bct, o_ab, o_abt, o_crw, o_ry2, o_bv, o_cid, o_b0, o_rho, o_pb0, o_ibv0,
+      o_cidu, o_rhou, o_b0u, o_w, o_ar, o_c0, o_rth;
   int smem_doubles, stride;
 };
 
@@ -134,8 +135,11 @@ template <class D>
 LinLayout layout_of() {
   LinLayout l;
   l.nx = D::NX; l.ny = D::NY; l.nz = D::NZ; l.nth = D::NTH; l.ncol = D::NCOL; l.nd = D::ND; l.group = D::G;
+  l.nr = D::NR; l.nrp = D::NRP; l.nfr = D::NFR;
   l.o_res = D::O_RES; l.o_ca2 = D::O_CA2; l.o_aibc = D::O_AIBC; l.o_aibr = D::O_AIBR; l.o_s0 = D::O_S0;
-  l.o_s0t = D::O_S0T; l.o_ry2 = D::O_RY2; l.o_w = D::O_W; l.o_ar = D::O_AR; l.o_c0 = D::O_C0; l.o_rth = D::O_RTH;
+  l.o_s0t = D::O_S0T; l.o_bc = D::O_BC; l.o_bct = D::O_BCT; l.o_crw = D::O_CRW; l.o_ry2 = D::O_RY2; l.o_bv = D::O_BV;
+  l.o_cid = D::O_CID; l.o_ab = D::O_AB; l.o_abt = D::O_ABT; l.o_b0 = D::O_B0; l.o_rho = D::O_RHO; l.o_pb0 = D::O_PB0;
+  l.o_ibv0 = D::O_IBV0; l.o_cidu = D::O_CIDU; l.o_rhou = D::O_RHOU; l.o_b0u = D::O_B0U; l.o_w = D::O_W; l.o_ar = D::O_AR; l.o_c0 = D::O_C0; l.o_rth = D::O_RTH;
   l.smem_doubles = D::SMEM_DOUBLES; l.stride = D::LIN_STRIDE;
   return l;
 }

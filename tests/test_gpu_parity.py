@@ -158,12 +158,15 @@ def test_ragged_and_tiny_batches(cuda_device, n):
 
 def test_hopper_smallest_group(cuda_device):
     """hopper_2D sizes (nx = ny = 4 → 4 lanes per problem, 8 problems per warp) on a synthetic
-    well-posed linearization: a random strictly monotone LCP-like block structure."""
+    well-posed linearization: a random strictly monotone LCP-like problem with the block structure of the contact
+    residual (simulation.jl:133-158: the fri row and the ψ column touch only the E / μ couplings), which the kernel's
+    closed-form elimination of ψ1 relies on — an upload WITHOUT that structure is refused."""
     import cimpc_b200 as cb
     from oracle.c_oracle import COracle
     rng = np.random.default_rng(5)
     nq, nu, nw, nc, nb = SIZES["hopper_2D"]
     nz, nth, ny = nq + 4 * nc + 2 * nb, 2 * nq + nu + nw + 2, 2 * nc + nb
+    nr = nc + nb
     H = 6
     z0 = np.abs(rng.standard_normal((H, nz))) + 0.5
     th0 = rng.standard_normal((H, nth))
@@ -173,15 +176,24 @@ def test_hopper_smallest_group(cuda_device):
     for t in range(H):
         A = rng.standard_normal((nq, nq))
         rz0[t, :nq, :nq] = A @ A.T + nq * np.eye(nq)                 # Dx
-        Jt = rng.standard_normal((nq, ny))
-        rz0[t, :nq, nq:nq + ny] = -Jt                                  # Dy1
-        rz0[t, nq:nq + ny, :nq] = Jt.T                                 # Rx
-        K = rng.standard_normal((ny, ny))
-        rz0[t, nq:nq + ny, nq:nq + ny] = 0.1 * (K - K.T)               # Ry1 (skew)
+        Jt = rng.standard_normal((nq, nr))
+        rz0[t, :nq, nq:nq + nr] = -Jt                                  # Dy1[:, γb]; Dy1[:, ψ] = 0
+        rz0[t, nq:nq + nr, :nq] = Jt.T                                 # Rx[imp ∪ mdp, :]; Rx[fri, :] = 0
+        K = rng.standard_normal((nr, nr))
+        rz0[t, nq:nq + nr, nq:nq + nr] = 0.1 * (K - K.T)               # Ry1[imp ∪ mdp, γb] (skew)
+        rz0[t, nq + nc:nq + nr, nq + nr] = -1.0                        # −Eᵀ: mdp rows ← ψ
+        rz0[t, nq + nr, nq:nq + nc] = -0.7                             # fri row: −μ γ
+        rz0[t, nq + nr, nq + nc:nq + nr] = 1.0                         #          + E b
         rz0[t, nq:nq + ny, nq + ny:] = np.eye(ny)                      # Ry2 = 1
         rz0[t, nq + ny:, nq:nq + ny] = np.diag(z0[t, nq + ny:])
         rz0[t, nq + ny:, nq + ny:] = np.diag(z0[t, nq:nq + ny])
         rth0[t, nq + ny:, :] = 0.0
+        rth0[t, nq + nr, :2 * nq + nu] = 0.0                           # the fri row depends on θ through μ only
+    bad = rz0.copy()
+    bad[:, nq + nr, nq + nr] = 0.3                                     # Ry1[fri, ψ] ≠ 0: not a contact residual
+    with pytest.raises(cb.CimpcError) as ei:
+        cb.ImplicitTrajectory(nq, nu, nw, nc, nb, z0, th0, r0, bad, rth0)
+    assert ei.value.code == 2
     lin = dict(z0=z0, th0=th0, r0=r0, rz0=rz0, rth0=rth0)
     for mode in ("configuration", "configurationforce"):
         opts = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=1e-6, diff_sol=True, max_ls=0)
