@@ -385,6 +385,10 @@ def main():
                "rollouts_per_gpu": Rm, "steps": m_steps, "ms_per_mpc_step_batch": float(tm.item()) / m_steps,
                "mean_newton_iterations": float(inf[0]), "mean_implicit_dynamics_sweeps": float(inf[1]),
                "converged_frac": float(inf[2]), "sweeps_per_call": newton.last_sweeps,
+               # one CUDA-graph launch per MPC step; its kernel nodes: reset + finish + 3 per sweep slot (unrolled to the
+               # reference's sweep bound 1 + 8·max_iter; slots after the last active rollout exit immediately)
+               "host_launch_calls_per_mpc_step": 1, "host_syncs_per_mpc_step": 0,
+               "gpu_kernels_doing_work_per_mpc_step": 2 + 3 * int(newton.last_sweeps),
                "gpu_launches": int(im.launch_count - l0),
                "config": "newton_solve! cold start, quadruped H_mpc=10, r_tol=3e-4, max_iter=5 (monte_carlo.jl:44-48), "
                          "q1 = reference + N(0, 0.01^2)"}

@@ -20,7 +20,8 @@ SYMBOLS = [
     "cimpc_ip_solve_batch", "cimpc_ip_solve_batch_host", "cimpc_launch_count",
     "cimpc_newton_opts_default", "cimpc_newton_create", "cimpc_newton_solve_batch", "cimpc_newton_last_sweeps",
     "cimpc_sim_step_batch", "cimpc_linearize", "cimpc_get_linearization",
-    "cimpc_newton_create_ex", "cimpc_newton_solve_batch_ex",
+    "cimpc_newton_create_ex", "cimpc_newton_solve_batch_ex", "cimpc_newton_solve_batch_ex2",
+    "cimpc_newton_solve_batch_host",
 ]
 
 
@@ -104,6 +105,11 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_newton_solve_batch_ex.argtypes = [vp, dp, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp, i32, dp, dp, dp,
                                                 dp, vp]
     lib.cimpc_newton_solve_batch_ex.restype = C.c_int
+    lib.cimpc_newton_solve_batch_ex2.argtypes = [vp, dp, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp, dp, i32, dp, dp,
+                                                 dp, dp, vp]
+    lib.cimpc_newton_solve_batch_ex2.restype = C.c_int
+    lib.cimpc_newton_solve_batch_host.argtypes = [vp, dp, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp, dp, i32, dp, dp]
+    lib.cimpc_newton_solve_batch_host.restype = C.c_int
     lib.cimpc_linearize.argtypes = [vp, i32, dp, dp, C.c_double, vp]
     lib.cimpc_linearize.restype = C.c_int
     lib.cimpc_get_linearization.argtypes = [vp, dp, dp, dp]

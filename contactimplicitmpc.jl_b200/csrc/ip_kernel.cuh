@@ -53,6 +53,15 @@ struct IpParams {
   const int32_t* __restrict__ act = nullptr;
   int32_t n_act = 0;
   int32_t R = 0;
+  // device-driven compaction (the newton_solve! graph, api.cu): when `par` is set, the list of this sweep is
+  // act2 + (*par)·R with cnt2[*par] entries and the launch covers stages·cnt2[*par] slots — nothing comes from the host
+  const int32_t* __restrict__ act2 = nullptr;
+  const int* __restrict__ cnt2 = nullptr;
+  const int* __restrict__ par = nullptr;
+  int32_t stages = 0;
+  // alt holds one row per ROLLOUT (subproblem index mod R) instead of one per subproblem: `set_altitude!` gives every
+  // stage of a policy the same offsets (src/controller/implicit_dynamics.jl:141-154)
+  int32_t alt_by_rollout = 0;
 };
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -584,15 +593,23 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
 
   // slot → subproblem (identity unless the launch is compacted).  32-bit arithmetic on purpose: a 64-bit division is
   // an out-of-line call in SASS, and with that call present this kernel computed garbage (bisected on B200, nvcc 12.9).
-  const int32_t* const act = p.act;
-  const int n_act = p.n_act, nroll = p.R;
+  const int32_t* act = p.act;
+  int n_act = p.n_act;
+  int64_t n_slots = p.n;
+  if (p.par != nullptr) {
+    const int cur = *p.par;
+    act = p.act2 + (size_t)cur * p.R;
+    n_act = p.cnt2[cur];
+    n_slots = (int64_t)p.stages * n_act;
+  }
+  const int nroll = p.R;
   auto sub = [=](int64_t slot) -> int64_t {
     if (act == nullptr) return slot;
     const unsigned s = (unsigned)slot, t = s / (unsigned)n_act;  // a compacted launch has < 2^31 slots
     return (int64_t)t * nroll + act[s - t * (unsigned)n_act];
   };
   // this CTA's contiguous slice of the batch
-  const int64_t c0 = p.n * (int64_t)blockIdx.x / gridDim.x, c1 = p.n * (int64_t)(blockIdx.x + 1) / gridDim.x;
+  const int64_t c0 = n_slots * (int64_t)blockIdx.x / gridDim.x, c1 = n_slots * (int64_t)(blockIdx.x + 1) / gridDim.x;
   if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
   int staged = -1;
@@ -683,7 +700,10 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
           cd = fma(r.x, t, cd);
           cr = fma(r.y, t, cr);
         }
-        if (p.alt != nullptr && l < NC) cr += p.alt[pi * NC + l];
+        if (p.alt != nullptr && l < NC) {
+          const int64_t arow = p.alt_by_rollout ? (int64_t)((unsigned)pi % (unsigned)nroll) : pi;  // 32-bit on purpose
+          cr += p.alt[arow * NC + l];
+        }
         c.cdyn = cd;
         c.crst = cr;
       }

@@ -49,8 +49,10 @@ __global__ void __launch_bounds__(THREADS) newton_step_general_kernel(const Newt
   constexpr int NB = SM::NB, BS = SM::BS, NRX = SM::NRX, DL = SM::DL;
   constexpr unsigned FULLM = 0xffffffffu;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, H = p.H, R = p.R;
-  const int r = blockIdx.x * (THREADS / 32) + wid;
-  if (r >= R) return;
+  const int cur = *p.par;
+  const int slot = blockIdx.x * (THREADS / 32) + wid;
+  if (slot >= p.act_count[cur]) return;
+  const int r = p.act_list[(size_t)cur * R + slot];
   const int phase = p.phase[r];
   if (phase == NP_DONE) return;
 
@@ -492,15 +494,15 @@ __global__ void __launch_bounds__(THREADS) newton_step_general_kernel(const Newt
     else if (c < 2 * NQ) v = cq[(t + 1) * NQ + c - NQ];
     else if (c < 2 * NQ + NU) v = cu[t * NU + c - 2 * NQ];
     else if (c < 2 * NQ + NU + NW) v = p.w[t * NW + c - 2 * NQ - NU];
-    else if (c == 2 * NQ + NU + NW) v = p.mu;
-    else v = p.h;
+    else if (c == 2 * NQ + NU + NW) v = p.call->mu;
+    else v = p.call->h;
     p.theta[((size_t)t * R + r) * NTH + c] = v;
   }
   for (int e = lane; e < H * NQ; e += 32) {
     const int t = e / NQ, k = e % NQ;
     p.q2[((size_t)t * R + r) * NQ + k] = cq[(t + 2) * NQ + k];
   }
-  if (lane == 0) p.act_list[atomicAdd(p.act_count, 1)] = r;
+  if (lane == 0) p.act_list[(size_t)(cur ^ 1) * R + atomicAdd(&p.act_count[cur ^ 1], 1)] = r;
 }
 
 }  // namespace cimpc

@@ -28,6 +28,22 @@ namespace cimpc {
 
 enum NewtonPhase : int { NP_INIT = 0, NP_LS = 1, NP_DONE = 2 };
 
+// Per-call arguments of one batched newton_solve! (device copy read by the reset / finish kernels of the solve graph,
+// so that the instantiated graph never changes).
+struct NewtonCall {
+  const double* q0;       // nq × R
+  const double* q1;       // nq × R
+  const uint8_t* active;  // R or null
+  const double* alt;      // nc × R per-rollout altitude offsets (policy.jl:111-115, update_altitude!), or null
+  double* u_out;          // nu × R
+  double* q_out;          // nq × (H+2) × R or null
+  double* y_out;          // nyd × H × R or null
+  int32_t* info;          // 4 × R or null
+  int32_t warm_start;
+  int32_t pad;
+  double mu, h;           // θ entries μ and h of this solve
+};
+
 struct NewtonParams {
   int R, H;
   // shared by every rollout (they track the same gait in lock-step, policy.jl:100-107, 131)
@@ -37,7 +53,8 @@ struct NewtonParams {
   const int32_t* window;  // H            knot of every stage
   const double* obj_q;    // H × nq       diagonal of obj.q[t]
   const double* obj_u;    // H × nu
-  double mu, h, kappa;
+  const NewtonCall* call; // per-call arguments (device)
+  double kappa;
   double r_tol, beta_init;
   int max_iter;
   // per rollout state
@@ -53,9 +70,14 @@ struct NewtonParams {
   const double* z;   // H×R×nz
   const double* dz;  // H×R×(nd×ncol), column-major per subproblem
   int* n_active;     // [1] rollouts still iterating (decremented when a rollout finishes)
-  // compaction of the next implicit_dynamics! sweep: the rollouts that asked for one (unordered), and their number
-  int32_t* act_list;  // R
-  int* act_count;     // [1] zeroed by the host before every newton_step / newton_reset launch
+  // compaction of the sweeps: two lists of rollouts (unordered) and their lengths.  List *par is the one the CURRENT
+  // sweep runs over (ip_solve_kernel and newton_step read it); rollouts that ask for another sweep append themselves to
+  // the other one; newton_advance_kernel flips `par` between sweeps.
+  int32_t* act_list;  // 2 × R
+  int* act_count;     // [2]
+  int* par;           // [1]
+  int* sweep_ctr;     // [1] sweeps done in this solve
+  double* alt;        // R × nc  altitude offsets of every rollout for this solve (zeros when the caller passes none)
   // general variant only (newton_general.cuh): contact forces y = [γ; b] as Newton variables (:configurationforce)
   // and the velocity weights of a TrackingVelocityObjective
   double *traj_y = nullptr, *cand_y = nullptr;  // R×H×nyd
@@ -94,8 +116,10 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
   constexpr int BS = SM::BS;
   constexpr unsigned FULLM = 0xffffffffu;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, H = p.H, R = p.R;
-  const int r = blockIdx.x * (THREADS / 32) + wid;
-  if (r >= R) return;
+  const int cur = *p.par;
+  const int slot = blockIdx.x * (THREADS / 32) + wid;
+  if (slot >= p.act_count[cur]) return;
+  const int r = p.act_list[(size_t)cur * R + slot];
   const int phase = p.phase[r];
   if (phase == NP_DONE) return;
 
@@ -445,25 +469,28 @@ __global__ void __launch_bounds__(THREADS) newton_step_kernel(const NewtonParams
     else if (c < 2 * NQ) v = cq[(t + 1) * NQ + c - NQ];
     else if (c < 2 * NQ + NU) v = cu[t * NU + c - 2 * NQ];
     else if (c < 2 * NQ + NU + NW) v = p.w[t * NW + c - 2 * NQ - NU];
-    else if (c == 2 * NQ + NU + NW) v = p.mu;
-    else v = p.h;
+    else if (c == 2 * NQ + NU + NW) v = p.call->mu;
+    else v = p.call->h;
     p.theta[((size_t)t * R + r) * NTH + c] = v;
   }
   for (int e = lane; e < H * NQ; e += 32) {
     const int t = e / NQ, k = e % NQ;
     p.q2[((size_t)t * R + r) * NQ + k] = cq[(t + 2) * NQ + k];
   }
-  if (lane == 0) p.act_list[atomicAdd(p.act_count, 1)] = r;  // this rollout takes part in the next sweep
+  if (lane == 0) p.act_list[(size_t)(cur ^ 1) * R + atomicAdd(&p.act_count[cur ^ 1], 1)] = r;  // takes part in the next sweep
 }
 
 // reset!  (newton.jl:130-167): traj ← ref (cold) ; q[1], q[2] ← q0, q1 ; candidate ← traj ; first sweep inputs.
 template <class D, int THREADS>
-__global__ void __launch_bounds__(THREADS) newton_reset_kernel(const NewtonParams p, const double* __restrict__ q0,
-                                                               const double* __restrict__ q1, int warm_start,
-                                                               const uint8_t* __restrict__ active) {
+__global__ void __launch_bounds__(THREADS) newton_reset_kernel(const NewtonParams p, const NewtonCall* __restrict__ call) {
   constexpr int NQ = D::NQ, NU = D::NU, NW = D::NW, ND = D::ND, NTH = D::NTH, NYD = D::NYD;
   const int r = blockIdx.x, tid = threadIdx.x, H = p.H, R = p.R;
   if (r >= R) return;
+  const double* __restrict__ q0 = call->q0;
+  const double* __restrict__ q1 = call->q1;
+  const uint8_t* __restrict__ active = call->active;
+  const int warm_start = call->warm_start;
+  const double* __restrict__ alt = call->alt;
   if constexpr (NYD > 0) {  // γ, b follow the reference on a cold start (newton.jl:139-151); candidate ← traj
     double* ty = p.traj_y + (size_t)r * H * NYD;
     double* cy = p.cand_y + (size_t)r * H * NYD;
@@ -500,20 +527,21 @@ __global__ void __launch_bounds__(THREADS) newton_reset_kernel(const NewtonParam
     else if (c < 2 * NQ) v = traj_q[(t + 1) * NQ + c - NQ];
     else if (c < 2 * NQ + NU) v = traj_u[t * NU + c - 2 * NQ];
     else if (c < 2 * NQ + NU + NW) v = p.w[t * NW + c - 2 * NQ - NU];
-    else if (c == 2 * NQ + NU + NW) v = p.mu;
-    else v = p.h;
+    else if (c == 2 * NQ + NU + NW) v = p.call->mu;
+    else v = p.call->h;
     p.theta[((size_t)t * R + r) * NTH + c] = v;
   }
   for (int e = tid; e < H * NQ; e += THREADS) {
     const int t = e / NQ, k = e % NQ;
     p.q2[((size_t)t * R + r) * NQ + k] = traj_q[(t + 2) * NQ + k];
   }
+  for (int e = tid; e < D::NC; e += THREADS) p.alt[(size_t)r * D::NC + e] = alt ? alt[(size_t)r * D::NC + e] : 0.0;
   const bool on = (active == nullptr) || active[r] != 0;  // inactive rollouts (ended simulations) are not solved
   for (int t = tid; t < H; t += THREADS) p.knot[(size_t)t * R + r] = on ? p.window[t] : -1;
   if (tid == 0) {
     p.phase[r] = on ? NP_INIT : NP_DONE;
     if (!on) atomicSub(p.n_active, 1);
-    else p.act_list[atomicAdd(p.act_count, 1)] = r;
+    else p.act_list[atomicAdd(&p.act_count[0], 1)] = r;  // list 0 is the first sweep's (par = 0 after the reset)
     p.alpha[r] = 1.0;
     p.beta[r] = p.beta_init;
     p.r_norm[r] = 0.0;

@@ -26,8 +26,7 @@ struct ModelEntry {
   cudaError_t (*launch)(const IpParams& p, int sm_count, cudaStream_t s);
   cudaError_t (*occupancy)(int* blocks_per_sm);
   // device Newton (:configuration instances only, else null)
-  cudaError_t (*newton_reset)(const NewtonParams& p, const double* q0, const double* q1, int warm,
-                              const uint8_t* active, cudaStream_t s);
+  cudaError_t (*newton_reset)(const NewtonParams& p, const NewtonCall* call, cudaStream_t s);
   cudaError_t (*newton_step)(const NewtonParams& p, double* lscratch, cudaStream_t s);
   size_t (*newton_scratch)(int H);  // doubles of global scratch per rollout
   // general device Newton (both modes; [0] TrackingObjective, [1] TrackingVelocityObjective)
@@ -64,9 +63,8 @@ struct SmemOptIn {
 };
 
 template <class D>
-cudaError_t launch_newton_reset(const NewtonParams& p, const double* q0, const double* q1, int warm,
-                                const uint8_t* active, cudaStream_t s) {
-  newton_reset_kernel<D, NEWTON_THREADS><<<p.R, NEWTON_THREADS, 0, s>>>(p, q0, q1, warm, active);
+cudaError_t launch_newton_reset(const NewtonParams& p, const NewtonCall* call, cudaStream_t s) {
+  newton_reset_kernel<D, NEWTON_THREADS><<<p.R, NEWTON_THREADS, 0, s>>>(p, call);
   return cudaGetLastError();
 }
 

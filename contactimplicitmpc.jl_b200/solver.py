@@ -245,10 +245,11 @@ class Newton:
             ov.ctypes.data if ov is not None else None, float(kappa), C.byref(co), C.byref(ci)))
 
     def solve(self, window, ref_q, ref_u, mu, h, q0, q1, warm_start=False, want_q=False, stream=None, active=None,
-              ref_gamma=None, ref_b=None, want_y=False):
+              ref_gamma=None, ref_b=None, want_y=False, alt=None):
         """window: (H+2,) 0-based knots; ref_q (H+2, nq), ref_u (H, nu) [, ref_gamma (H, nc), ref_b (H, nb)] host arrays
         (shared by all rollouts); q0, q1: torch CUDA (R, nq) fp64.  Returns u (R, nu), q (R, H+2, nq) or None, info (R, 4)
-        int32 [Newton iterations, sweeps, converged, phase] as torch CUDA tensors (and y (R, H, nc+nb) with want_y)."""
+        int32 [Newton iterations, sweeps, converged, phase] as torch CUDA tensors (and y (R, H, nc+nb) with want_y).
+        alt: torch CUDA (R, nc) altitude offsets of every rollout (`p.altitude`, policy.jl:111-115) or None."""
         import torch
         im = self.im
         window = np.ascontiguousarray(window, dtype=np.int32)
@@ -264,22 +265,50 @@ class Newton:
         dev = q0.device
         if active is not None:
             assert active.dtype == torch.uint8 and active.is_cuda and active.is_contiguous() and active.shape == (self.R,)
+        if alt is not None:
+            assert alt.dtype == torch.float64 and alt.is_cuda and alt.is_contiguous() and alt.shape == (self.R, im.nc)
         u = torch.empty((self.R, im.nu), dtype=torch.float64, device=dev)
         q = torch.empty((self.R, self.H + 2, im.nq), dtype=torch.float64, device=dev) if want_q else None
         y = torch.empty((self.R, self.H, im.nc + im.nb), dtype=torch.float64, device=dev) if (want_y and self.force) else None
         info = torch.empty((self.R, 4), dtype=torch.int32, device=dev)
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
-        capi.check(im._ctx, im.lib.cimpc_newton_solve_batch_ex(
+        capi.check(im._ctx, im.lib.cimpc_newton_solve_batch_ex2(
             im._ctx, window.ctypes.data, ref_q.ctypes.data, ref_u.ctypes.data,
             rg.ctypes.data if rg is not None else None, rb.ctypes.data if rb is not None else None,
             float(mu), float(h), q0.data_ptr(),
-            q1.data_ptr(), active.data_ptr() if active is not None else None, int(bool(warm_start)), u.data_ptr(),
+            q1.data_ptr(), active.data_ptr() if active is not None else None,
+            alt.data_ptr() if alt is not None else None, int(bool(warm_start)), u.data_ptr(),
             q.data_ptr() if q is not None else None, y.data_ptr() if y is not None else None,
             info.data_ptr(), C.c_void_p(stream)))
         if want_y:
             return u, q, info, y
         return u, q, info
+
+    def solve_host(self, window, ref_q, ref_u, mu, h, q0, q1, warm_start=False, active=None, ref_gamma=None, ref_b=None,
+                   alt=None, u_out=None, info_out=None):
+        """`newton_solve!` for every rollout with HOST arrays (numpy, or numpy views of pinned torch tensors): q0, q1
+        (R, nq) in, u (R, nu) and info (R, 4) out, through `cimpc_newton_solve_batch_host`."""
+        im = self.im
+        window = np.ascontiguousarray(window, dtype=np.int32)
+        ref_q = _f64(ref_q, (self.H + 2, im.nq))
+        ref_u = _f64(ref_u, (self.H, im.nu))
+        rg = _f64(ref_gamma, (self.H, im.nc)) if self.force else None
+        rb = _f64(ref_b, (self.H, im.nb)) if self.force else None
+        for a in (q0, q1):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape == (self.R, im.nq)
+        u = u_out if u_out is not None else np.empty((self.R, im.nu))
+        info = info_out if info_out is not None else np.empty((self.R, 4), dtype=np.int32)
+        if active is not None:
+            active = np.ascontiguousarray(active, dtype=np.uint8)
+        if alt is not None:
+            alt = _f64(alt, (self.R, im.nc))
+        capi.check(im._ctx, im.lib.cimpc_newton_solve_batch_host(
+            im._ctx, window.ctypes.data, ref_q.ctypes.data, ref_u.ctypes.data,
+            rg.ctypes.data if rg is not None else None, rb.ctypes.data if rb is not None else None, float(mu), float(h),
+            q0.ctypes.data, q1.ctypes.data, active.ctypes.data if active is not None else None,
+            alt.ctypes.data if alt is not None else None, int(bool(warm_start)), u.ctypes.data, info.ctypes.data))
+        return u, info
 
     @property
     def last_sweeps(self) -> int:

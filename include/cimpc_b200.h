@@ -212,7 +212,7 @@ int cimpc_newton_create(cimpc_ctx* ctx, int32_t H_mpc, int64_t n_rollouts, const
  *   u_out    nu × n_rollouts       `core.traj.u[1]`  (the policy returns it divided by N_sample, policy.jl:141-144)
  *   q_out    nq × (H_mpc+2) × n_rollouts   optimised configurations `core.traj.q`, or NULL
  *   info     4 × n_rollouts int32  [Newton iterations, implicit_dynamics! sweeps, converged(0/1), reserved], or NULL
- * The call runs asynchronously on `stream` except for one 4-byte read per sweep (termination test).
+ * The call is asynchronous on `stream` (one CUDA-graph launch, see cimpc_newton_solve_batch_ex2).
  */
 int cimpc_newton_solve_batch(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
                              double mu, double h, const double* q0, const double* q1, const uint8_t* active,
@@ -254,7 +254,33 @@ int cimpc_newton_solve_batch_ex(cimpc_ctx* ctx, const int32_t* window, const dou
                                 const double* q1, const uint8_t* active, int32_t warm_start, double* u_out,
                                 double* q_out, double* y_out, int32_t* info, void* stream);
 
-/* Sweeps (= ip_solve_kernel launches) used by the last cimpc_newton_solve_batch call. */
+/*
+ * Same call with per-rollout ALTITUDE offsets: `alt` nc × n_rollouts DEVICE or NULL — `p.altitude` of every rollout's
+ * policy, applied to the impact rows of all stages (`set_altitude!(p.im_traj, p.altitude)`, src/controller/policy.jl:111-115,
+ * src/controller/implicit_dynamics.jl:141-154; `rlin!`, src/controller/linearized_solver.jl:370).
+ *
+ * Execution.  One call = ONE CUDA-graph launch: newton_reset → (1 + 8·max_iter) × { ip_solve (compacted to the rollouts
+ * that still iterate, sizes read on the device) → newton_step → advance } → newton_finish.  The sweep bound is the
+ * reference's own (newton.jl:202-269); sweeps after the last rollout has finished exit at once.  No host synchronisation
+ * between `implicit_dynamics!` sweeps: the call is fully asynchronous on `stream`.
+ */
+int cimpc_newton_solve_batch_ex2(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
+                                 const double* ref_gamma, const double* ref_b, double mu, double h, const double* q0,
+                                 const double* q1, const uint8_t* active, const double* alt, int32_t warm_start,
+                                 double* u_out, double* q_out, double* y_out, int32_t* info, void* stream);
+
+/*
+ * The same MPC step with HOST buffers (what `policy(p, traj, t)` exchanges with its caller, policy.jl:118-120, 141-144):
+ * q0, q1 nq × n_rollouts, active (uint8) / alt (nc × n_rollouts) or NULL in; u_out nu × n_rollouts, info 4 × n_rollouts
+ * (or NULL) out.  (2 nq + nu)·8 bytes per rollout cross the bus; the call returns when u_out is valid.  Page-locked
+ * caller buffers are used in place, pageable ones are staged.
+ */
+int cimpc_newton_solve_batch_host(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
+                                  const double* ref_gamma, const double* ref_b, double mu, double h, const double* q0,
+                                  const double* q1, const uint8_t* active, const double* alt, int32_t warm_start,
+                                  double* u_out, int32_t* info);
+
+/* `implicit_dynamics!` sweeps (= iterations of the graph's loop) of the last solve; synchronises with the device. */
 int32_t cimpc_newton_last_sweeps(const cimpc_ctx* ctx);
 
 /* Number of kernel launches issued through this context so far (bench bookkeeping). */
