@@ -7,3 +7,5 @@ from .solver import (ImplicitTrajectory, InteriorPointOptions, Newton, NewtonOpt
 from .sharding import gather_rollout_results, shard_rollouts, sum_statistics  # noqa: F401,E402
 from .rollout import GroupedRollouts, MonteCarloRollouts, ReferenceWindow, quadruped_initial_configurations  # noqa: F401,E402
 from .trajectory import ContactTraj, JLD2File, load_gait, load_traj, repeat_ref_traj, save_traj, tracking_error  # noqa: F401,E402
+from .disturbances import (Disturbances, EmptyDisturbances, ImpulseDisturbance, OpenLoopDisturbance,  # noqa: F401,E402
+                           RandomDisturbance)

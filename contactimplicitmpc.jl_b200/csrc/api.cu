@@ -1066,6 +1066,12 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const doub
                          const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts, double* q2, double* gamma,
                          double* b,
                          uint8_t* status, int32_t* iters, void* stream) {
+  return cimpc_sim_step_batch_ex(ctx, n, q0, q1, u, w, active, mu, h, opts, q2, gamma, b, nullptr, status, iters, stream);
+}
+
+int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n, const double* q0, const double* q1, const double* u, const double* w,
+                            const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts, double* q2,
+                            double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters, void* stream) {
   if (!ctx || n < 0 || n > (1 << 30) || !opts) return CIMPC_ERR_INVALID_ARGUMENT;
   if (n == 0) return CIMPC_OK;
   if (!q0 || !q1 || !u || !q2 || !gamma || !b || !status || !iters) return CIMPC_ERR_INVALID_ARGUMENT;
@@ -1079,7 +1085,7 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const doub
   }
   SimParams p;
   p.R = (int)n; p.q0 = q0; p.q1 = q1; p.u = u; p.w = w; p.active = active; p.mu = mu; p.h = h; p.o = *opts;
-  p.q2_out = q2; p.gamma_out = gamma; p.b_out = b; p.status = status; p.iters = iters; p.scratch = ctx->sim_scratch;
+  p.q2_out = q2; p.gamma_out = gamma; p.b_out = b; p.phi_out = phi; p.status = status; p.iters = iters; p.scratch = ctx->sim_scratch;
   cudaError_t e = ctx->entry->sim_step(p, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "sim_step_kernel launch");
   ctx->launches++;

@@ -45,6 +45,7 @@ struct SimParams {
   double* q2_out;     // nq × R   q_{t+2}
   double* gamma_out;  // nc × R
   double* b_out;      // nb × R
+  double* phi_out;    // nc × R or null: s1 = ϕ(q_{t+2}) of the solution (signed distances, for `update_altitude!`)
   uint8_t* status;    // R
   int32_t* iters;     // R
   double* scratch;    // per tile of 32 rollouts: SimLayout::TILE × 32 doubles
@@ -514,6 +515,8 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
     for (int e = 0; e < NQ; ++e) p.q2_out[(size_t)rr * NQ + e] = S(L::O_Z, e);
     for (int e = 0; e < NC; ++e) p.gamma_out[(size_t)rr * NC + e] = S(L::O_Z, NQ + e);
     for (int e = 0; e < NB; ++e) p.b_out[(size_t)rr * NB + e] = S(L::O_Z, NQ + NC + e);
+    if (p.phi_out != nullptr)
+      for (int e = 0; e < NC; ++e) p.phi_out[(size_t)rr * NC + e] = S(L::O_Z, NQ + 2 * NC + NB + e);
   }
 }
 

@@ -58,21 +58,29 @@ class MonteCarloRollouts:
     def __init__(self, im_traj: ImplicitTrajectory, ref_q, ref_u, mu_mpc, mu_sim, h, *, H_mpc, N_sample, obj_q, obj_u,
                  kappa, n_rollouts, newton_opts: NewtonOptions | None = None,
                  sim_opts: InteriorPointOptions | None = None, obj_gamma=None, obj_b=None, obj_v=None,
-                 ref_gamma=None, ref_b=None):
+                 ref_gamma=None, ref_b=None, altitude_update: bool = False, altitude_impact_threshold: float = 1.0,
+                 **newton_kw):
         """obj_gamma / obj_b / ref_gamma / ref_b: required when `im_traj.mode == "configurationforce"`;
-        obj_v: velocity weights of a TrackingVelocityObjective (the flamingo policy, examples/flamingo/flat.jl:34-41)."""
+        obj_v: velocity weights of a TrackingVelocityObjective (the flamingo policy, examples/flamingo/flat.jl:34-41);
+        altitude_update / altitude_impact_threshold: `CIMPCOptions` (src/controller/policy.jl:1-14) — every policy
+        keeps an altitude per contact, refreshed before each `newton_solve!` from the simulator step of largest impact
+        of the last N_sample steps (`update_altitude!`, src/controller/mpc_utils.jl:109-135) and added to the impact
+        rows of every stage (`set_altitude!`); examples/flamingo/piecewise.jl:37-47 uses threshold 0.02."""
         self.im, self.R, self.N, self.H = im_traj, int(n_rollouts), int(N_sample), int(H_mpc)
         self.h, self.mu_mpc, self.mu_sim = float(h), float(mu_mpc), float(mu_sim)
         self.ref = ReferenceWindow(ref_q, ref_u, H_mpc, ref_gamma, ref_b)
         self.newton = Newton(im_traj, H_mpc, n_rollouts, obj_q, obj_u, kappa, newton_opts, obj_gamma=obj_gamma,
-                             obj_b=obj_b, obj_v=obj_v)
+                             obj_b=obj_b, obj_v=obj_v, **newton_kw)
+        self.altitude_update, self.alt_threshold = bool(altitude_update), float(altitude_impact_threshold)
         self.sim = Simulator(im_traj.nq, im_traj.nu, im_traj.nw, im_traj.nc, im_traj.nb, opts=sim_opts or simulator_options(),
                              device=im_traj.device)
         self.mpc_steps = 0
 
-    def run(self, q1, v1, H_sim, record_every: int = 1):
+    def run(self, q1, v1, H_sim, record_every: int = 1, dist=None):
         """q1, v1: torch CUDA (R, nq).  Returns dict of torch CUDA tensors q (T+2, R, nq), u, gamma, b (T, R, ·)
-        sampled every `record_every` simulator steps (1 = everything), and status (R,) bool."""
+        sampled every `record_every` simulator steps (1 = everything), and status (R,) bool.
+        dist: a `disturbances.Disturbances` (`sim.dist`, src/simulator/disturbances.jl): w of every simulator step, the
+        same for all rollouts ((nw,) rows) or per rollout ((R, nw))."""
         import torch
         R, N = self.R, self.N
         dev = q1.device
@@ -93,19 +101,39 @@ class MonteCarloRollouts:
         cnt = N
         u_sim = torch.zeros((R, nu), dtype=torch.float64, device=dev)
         self.mpc_steps = 0
+        # `p.altitude` of every rollout, and the impact bookkeeping of `update_altitude!` over the last N simulator
+        # steps: largest normal impulse per contact and ϕ(q_{t+2}) at that step
+        alt = torch.zeros((R, nc), dtype=torch.float64, device=dev) if self.altitude_update else None
+        g_max = torch.zeros((R, nc), dtype=torch.float64, device=dev)
+        phi_at = torch.zeros((R, nc), dtype=torch.float64, device=dev)
+        out["alt"] = alt
         for t in range(1, H_sim + 1):
             if cnt == N:
+                if self.altitude_update and t > 1:  # policy.jl:111-115
+                    hit = g_max > self.alt_threshold
+                    alt = torch.where(hit, phi_at, alt).contiguous()
+                    out["alt"] = alt
+                g_max.zero_()
                 u_mpc, _, _ = self.newton.solve(self.ref.window, self.ref.q[:self.H + 2], self.ref.u[:self.H], self.mu_mpc,
                                                 self.h, q0_mpc, qb, warm_start=t > 1, active=ok.to(torch.uint8),
                                                 ref_gamma=None if self.ref.gamma is None else self.ref.gamma[:self.H],
-                                                ref_b=None if self.ref.b is None else self.ref.b[:self.H])
+                                                ref_b=None if self.ref.b is None else self.ref.b[:self.H], alt=alt)
                 u_sim = (u_mpc / N).contiguous()
                 self.ref.advance()
                 q0_mpc = qb
                 cnt = 0
                 self.mpc_steps += 1
             cnt += 1
-            q2, gam, b, st, _ = self.sim.step(qa, qb, u_sim, self.mu_sim, h_sim, active=ok.to(torch.uint8))
+            w = None
+            if dist is not None:
+                wt = np.asarray(dist(t), dtype=np.float64)
+                w = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(wt, (R, self.im.nw)))).to(dev)
+            q2, gam, b, st, _, phi = self.sim.step(qa, qb, u_sim, self.mu_sim, h_sim, w=w, active=ok.to(torch.uint8),
+                                                   want_phi=True)
+            if self.altitude_update:  # first maximum wins (strict `>` in mpc_utils.jl:119)
+                better = gam > g_max
+                g_max = torch.where(better, gam, g_max)
+                phi_at = torch.where(better, phi, phi_at)
             # a failed step ends that rollout (RoboDojo `simulate!` stops and returns false): it is frozen and
             # skipped by both kernels from here on
             st = st.bool() | ~ok

@@ -345,9 +345,11 @@ class Simulator:
         except Exception:
             pass
 
-    def step(self, q0, q1, u, mu, h, w=None, opts: InteriorPointOptions | None = None, stream=None, active=None):
+    def step(self, q0, q1, u, mu, h, w=None, opts: InteriorPointOptions | None = None, stream=None, active=None,
+             want_phi=False):
         """q0, q1 (R, nq), u (R, nu), w (R, nw) or None: torch CUDA fp64, contiguous.
-        Returns q2 (R, nq), gamma (R, nc), b (R, nb), status (R,) uint8, iters (R,) int32."""
+        Returns q2 (R, nq), gamma (R, nc), b (R, nb), status (R,) uint8, iters (R,) int32 (and phi (R, nc) = ϕ(q2) with
+        want_phi, the quantity `update_altitude!` samples)."""
         import torch
         o = opts or self.opts
         R = q0.shape[0]
@@ -363,10 +365,16 @@ class Simulator:
         if stream is None:
             stream = torch.cuda.current_stream(dev).cuda_stream
         co = o.to_c()
-        capi.check(self._ctx, self.lib.cimpc_sim_step_batch(
+        phi = torch.zeros((R, self.nc), dtype=torch.float64, device=dev) if want_phi else None
+        if w is not None:
+            assert w.is_cuda and w.dtype == torch.float64 and w.is_contiguous() and w.shape == (R, self.nw)
+        capi.check(self._ctx, self.lib.cimpc_sim_step_batch_ex(
             self._ctx, R, q0.data_ptr(), q1.data_ptr(), u.data_ptr(), w.data_ptr() if w is not None else None,
-            active.data_ptr() if active is not None else None, float(mu), float(h), C.byref(co), q2.data_ptr(), gam.data_ptr(), b.data_ptr(), st.data_ptr(),
-            it.data_ptr(), C.c_void_p(stream)))
+            active.data_ptr() if active is not None else None, float(mu), float(h), C.byref(co), q2.data_ptr(),
+            gam.data_ptr(), b.data_ptr(), phi.data_ptr() if phi is not None else None, st.data_ptr(), it.data_ptr(),
+            C.c_void_p(stream)))
+        if want_phi:
+            return q2, gam, b, st, it, phi
         return q2, gam, b, st, it
 
 

@@ -233,6 +233,14 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n_rollouts, const double* q0, c
                          const double* w, const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts,
                          double* q2, double* gamma, double* b, uint8_t* status, int32_t* iters, void* stream);
 
+/* Same step with one more output: phi nc × n DEVICE or NULL — the signed distances ϕ(q_{t+2}) of the solution (the
+ * slack s1 of the converged point), what `update_altitude!` reads at the step of largest impact
+ * (src/controller/mpc_utils.jl:109-135: `s.ϕ(ϕ, traj.q[idx_max+2])`). */
+int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n_rollouts, const double* q0, const double* q1, const double* u,
+                            const double* w, const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts,
+                            double* q2, double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters,
+                            void* stream);
+
 /*
  * General form of the two calls above: both modes of `ImplicitTrajectory` and both objectives.
  *   obj_gamma nc × H_mpc, obj_b nb × H_mpc   diagonals of `obj.γ[t]`, `obj.b[t]` — required in :configurationforce mode,

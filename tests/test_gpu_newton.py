@@ -32,7 +32,7 @@ def _objective(m):
     return oq, ou
 
 
-def _oracle_newton(m, lin, gait, ip_kw, n_opts):
+def _oracle_newton(m, lin, gait, ip_kw, n_opts, alt=None):
     from oracle.c_oracle import COracle
     from oracle.ip import IPOptions
     from oracle.newton import Newton, NewtonOptions, TrackingObjective
@@ -42,7 +42,9 @@ def _oracle_newton(m, lin, gait, ip_kw, n_opts):
 
     def dyn(window, traj):
         knot = np.array(window[:H_MPC], dtype=np.int32)
-        z, dz, st, it = co.solve(knot, traj.theta[:H_MPC], traj.q[2:H_MPC + 2], ipo)
+        # `set_altitude!`: the same offsets on every stage of the policy (implicit_dynamics.jl:141-154)
+        z, dz, st, it = co.solve(knot, traj.theta[:H_MPC], traj.q[2:H_MPC + 2], ipo,
+                                 alt=None if alt is None else np.tile(alt, (H_MPC, 1)))
         return z[:, :nq] - traj.q[2:H_MPC + 2], dz[:, :, :nq], dz[:, :, nq:2 * nq], dz[:, :, 2 * nq:]
 
     oq, ou = _objective(m)
@@ -86,6 +88,47 @@ def test_newton_solve_matches_oracle(cuda_device):
         assert bool(info[r, 2]) == bool(conv)
     assert agree >= R - 1, f"only {agree}/{R} rollouts followed the oracle's iteration path"
     assert worst_u <= 1e-7 and worst_q <= 1e-7, (worst_u, worst_q)
+
+
+def test_newton_solve_with_altitude_matches_oracle(cuda_device):
+    """`policy` with `altitude_update` (policy.jl:111-115): every rollout carries its own altitude vector, applied to the
+    impact rows of all H_mpc subproblems; device `newton_solve!` vs the oracle with the same offsets — and through the
+    HOST entry point (`cimpc_newton_solve_batch_host`), which must return the very same controls."""
+    import torch
+    import cimpc_b200 as cb
+    m, lin, gait, ref = _reference_traj("quadruped")
+    ip_kw = dict(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, max_ls=0)
+    n_opts = dict(r_tol=3e-4, max_iter=5)
+    R = 10
+    rng = np.random.default_rng(31)
+    q0 = np.tile(ref.q[0], (R, 1))
+    q1 = ref.q[1] + 0.005 * rng.standard_normal((R, m.nq))
+    alt = 0.01 * rng.random((R, m.nc))          # terrain up to 1 cm above the reference's ground
+    alt[0] = 0.0
+    window = np.arange(H_MPC + 2, dtype=np.int32)
+    im = cb.ImplicitTrajectory(*SIZES["quadruped"], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
+                               mode="configuration", opts=cb.InteriorPointOptions(diff_sol=True, **ip_kw))
+    oq, ou = _objective(m)
+    nw = cb.Newton(im, H_MPC, R, oq, ou, KAPPA, cb.NewtonOptions(**n_opts))
+    u, q, info = nw.solve(window, ref.q[:H_MPC + 2], ref.u[:H_MPC], gait["mu"], gait["h"],
+                          torch.from_numpy(q0).to(cuda_device), torch.from_numpy(q1).to(cuda_device), want_q=True,
+                          alt=torch.from_numpy(alt).to(cuda_device))
+    torch.cuda.synchronize()
+    u, q, info = u.cpu().numpy(), q.cpu().numpy(), info.cpu().numpy()
+    u_flat, _, _ = nw.solve(window, ref.q[:H_MPC + 2], ref.u[:H_MPC], gait["mu"], gait["h"],
+                            torch.from_numpy(q0).to(cuda_device), torch.from_numpy(q1).to(cuda_device))
+    u_flat = u_flat.cpu().numpy()
+    assert np.array_equal(u_flat[0], u[0]) and np.abs(u_flat[1:] - u[1:]).max() > 1e-4  # the offsets matter
+    agree = 0
+    for r in range(R):
+        core, dyn = _oracle_newton(m, lin, gait, ip_kw, n_opts, alt=alt[r])
+        uo = core.solve(dyn, q0[r], q1[r], list(window), ref, warm_start=False)
+        if core.stats["iters"] == info[r, 0] and core.stats["ip_sweeps"] == info[r, 1]:
+            agree += 1
+            assert np.abs(u[r] - uo).max() <= 1e-7 and np.abs(q[r] - core.traj.q).max() <= 1e-7
+    assert agree >= R - 1
+    uh, ih = nw.solve_host(window, ref.q[:H_MPC + 2], ref.u[:H_MPC], gait["mu"], gait["h"], q0, q1, alt=alt)
+    assert np.array_equal(uh, u) and np.array_equal(ih, info)
 
 
 def test_newton_warm_start_and_mpc_loop(cuda_device):

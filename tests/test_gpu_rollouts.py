@@ -104,6 +104,62 @@ def test_flamingo_closed_loop_on_device(cuda_device):
     assert (e[0] < band).all()  # the nominal rollout = the reference's own test
 
 
+def test_altitude_update_and_disturbances_in_the_loop(cuda_device):
+    """examples/flamingo/piecewise.jl:37-47 options on the device loop: `altitude_update = true`,
+    `altitude_impact_threshold = 0.02` — every rollout's altitude vector is refreshed from the simulator step of
+    largest impact of the last N_sample steps (mpc_utils.jl:109-135) — plus an impulse disturbance
+    (src/simulator/disturbances.jl:41-61) on the simulator's w.  Checked against a host re-computation of
+    `update_altitude!` from the recorded trajectory, and the disturbed rollouts must differ from the undisturbed run."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait
+    from oracle.residual import get_residual
+    from oracle.trajectory import phi_numeric, trajectory_from_gait
+    robot, H_mpc, N, kappa, H_sim, R = "flamingo", 15, 5, 1.0e-4, 120, 6
+    res = get_residual(robot)
+    m = res.model
+    gait = load_gait(robot)
+    ref = trajectory_from_gait(m, gait)
+    h = gait["h"]
+    ipo = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=kappa, undercut=5.0, diff_sol=True)
+    oq = np.tile(1e-1 * np.array([3e2, 1e-6, 3e2, 1, 1, 1, 1, 0.1, 0.1]), (H_mpc, 1))
+    ou = np.tile(3e-1 * np.array([0.1, 0.1, 0.3, 0.3, 2, 2]), (H_mpc, 1))
+    ov = np.tile(1e-3 * np.array([1e0, 1, 1e4, 1, 1, 1, 1, 1e4, 1e4]), (H_mpc, 1))
+    sim_opts = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=1e-8, max_ls=25, eps_min=0.05, undercut=float("inf"), gamma_reg=0.0)
+
+    def loop(dist):
+        im = cb.ImplicitTrajectory(*SIZES[robot], ref.z, ref.theta, kappa=kappa, mode="configurationforce", opts=ipo)
+        mc = cb.MonteCarloRollouts(im, ref.q, ref.u, ref.theta[0, -2], m.mu_world, h, H_mpc=H_mpc, N_sample=N, obj_q=oq,
+                                   obj_u=ou, kappa=kappa, n_rollouts=R, newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5),
+                                   sim_opts=sim_opts, obj_gamma=np.full((H_mpc, m.nc), 1e-100),
+                                   obj_b=np.full((H_mpc, m.nb), 1e-100), obj_v=ov, ref_gamma=ref.gamma, ref_b=ref.b,
+                                   altitude_update=True, altitude_impact_threshold=0.02)
+        q1 = np.tile(ref.q[1], (R, 1))
+        v1 = np.tile((ref.q[1] - ref.q[0]) / h, (R, 1))
+        out = mc.run(torch.from_numpy(q1).to(cuda_device), torch.from_numpy(v1).to(cuda_device), H_sim, dist=dist)
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items() if v is not None}
+
+    a = loop(None)
+    assert a["status"].all()
+    # host re-computation of update_altitude! at the last policy call (t = H_sim − N + 1) for rollout 0
+    alt = np.zeros(m.nc)
+    for t in range(1, H_sim + 1):
+        if (t - 1) % N == 0 and t > 1:
+            lo = max(0, t - 1 - N) + 1
+            for i in range(m.nc):
+                g = a["gamma"][lo - 1:t - 1, 0, i]
+                if g.max() > 0.02:
+                    j = lo + int(np.argmax(g))                    # 1-based simulator step of the largest impact
+                    alt[i] = phi_numeric(m, a["q"][j + 1, 0])[i]  # ϕ(traj.q[j + 2]) (1-based) = q array index j + 1
+    assert np.abs(a["alt"][0] - alt).max() < 1e-7, (a["alt"][0], alt)
+    assert np.abs(a["alt"]).max() < 5e-3          # flat ground: the measured altitudes are contact-level heights
+    # an impulse on the simulator's w at step 20 (w enters the dynamics through A(q)ᵀ w, model.jl:33)
+    b = loop(cb.ImpulseDisturbance([[2.0, 0.0]], [20]))
+    assert np.array_equal(a["q"][:20], b["q"][:20])
+    assert np.abs(a["q"][25] - b["q"][25]).max() > 1e-4
+
+
 def test_grouped_rollouts_are_bit_identical(cuda_device):
     """`GroupedRollouts` (independent parts on their own streams / host threads) changes scheduling only."""
     import torch
