@@ -21,7 +21,7 @@ SYMBOLS = [
     "cimpc_newton_opts_default", "cimpc_newton_create", "cimpc_newton_solve_batch", "cimpc_newton_last_sweeps",
     "cimpc_sim_step_batch", "cimpc_linearize", "cimpc_get_linearization",
     "cimpc_newton_create_ex", "cimpc_newton_solve_batch_ex", "cimpc_newton_solve_batch_ex2",
-    "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex",
+    "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex", "cimpc_newton_create_dense",
 ]
 
 
@@ -105,6 +105,9 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_newton_create_ex.argtypes = [vp, i32, i64, dp, dp, dp, dp, dp, C.c_double, C.POINTER(NewtonOpts),
                                            C.POINTER(IPOpts)]
     lib.cimpc_newton_create_ex.restype = C.c_int
+    lib.cimpc_newton_create_dense.argtypes = [vp, i32, i64, dp, dp, dp, dp, C.c_double, C.POINTER(NewtonOpts),
+                                              C.POINTER(IPOpts)]
+    lib.cimpc_newton_create_dense.restype = C.c_int
     lib.cimpc_newton_solve_batch_ex.argtypes = [vp, dp, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp, i32, dp, dp, dp,
                                                 dp, vp]
     lib.cimpc_newton_solve_batch_ex.restype = C.c_int

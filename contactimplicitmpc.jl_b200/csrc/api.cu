@@ -1,5 +1,6 @@
 // C ABI (include/cimpc_b200.h): context, linearization upload + set-up kernel, batched solves.
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -430,7 +431,9 @@ static int newton_sweep_launch(cimpc_ctx* ctx, cudaStream_t s) {
   ip.act2 = p.act_list; ip.cnt2 = p.act_count; ip.par = p.par; ip.stages = p.H;
   cudaError_t e = ctx->entry->launch(ip, ctx->sm_count, s);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "ip_solve_kernel launch");
-  e = nw.variant < 0 ? ctx->entry->newton_step(p, nw.lscratch, s) : ctx->entry->newton_step_g[nw.variant](p, nw.lscratch, s);
+  e = nw.variant < 0 ? ctx->entry->newton_step(p, nw.lscratch, s)
+      : (nw.variant < 2 ? ctx->entry->newton_step_g[nw.variant](p, nw.lscratch, s)
+                        : ctx->entry->newton_step_d[nw.variant - 2](p, nw.lscratch, s));
   if (e != cudaSuccess) return cuda_fail(ctx, e, "newton_step_kernel launch");
   newton_advance_kernel<<<1, 1, 0, s>>>(p);
   CK(cudaGetLastError());
@@ -812,20 +815,79 @@ int32_t cimpc_newton_last_sweeps(const cimpc_ctx* ctx) {
   return v;
 }
 
+// Cholesky Q = L Lᵀ of one nq×nq column-major SPD matrix and E = L⁻ᵀ (upper triangular); false if not SPD.
+static bool whitening_factor(int nq, const double* Q, double* E) {
+  std::vector<double> L((size_t)nq * nq, 0.0), Li((size_t)nq * nq, 0.0);
+  for (int j = 0; j < nq; ++j) {
+    double d = Q[j + (size_t)j * nq];
+    for (int k = 0; k < j; ++k) d -= L[j + (size_t)k * nq] * L[j + (size_t)k * nq];
+    if (!(d > 0.0)) return false;
+    const double ljj = std::sqrt(d);
+    L[j + (size_t)j * nq] = ljj;
+    for (int i = j + 1; i < nq; ++i) {
+      double v = Q[i + (size_t)j * nq];
+      for (int k = 0; k < j; ++k) v -= L[i + (size_t)k * nq] * L[j + (size_t)k * nq];
+      L[i + (size_t)j * nq] = v / ljj;
+    }
+  }
+  for (int j = 0; j < nq; ++j) {  // Li = L⁻¹ (lower triangular), column by column
+    Li[j + (size_t)j * nq] = 1.0 / L[j + (size_t)j * nq];
+    for (int i = j + 1; i < nq; ++i) {
+      double v = 0.0;
+      for (int k = j; k < i; ++k) v -= L[i + (size_t)k * nq] * Li[k + (size_t)j * nq];
+      Li[i + (size_t)j * nq] = v / L[i + (size_t)i * nq];
+    }
+  }
+  for (int i = 0; i < nq; ++i)
+    for (int j = 0; j < nq; ++j) E[i + (size_t)j * nq] = Li[j + (size_t)i * nq];  // E = Liᵀ
+  return true;
+}
+
+static int newton_create_impl(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q, const double* obj_qd,
+                              const double* obj_u, const double* obj_gamma, const double* obj_b, const double* obj_v,
+                              const double* v_target, double kappa, const cimpc_newton_opts* nopts,
+                              const cimpc_ip_opts* ip_opts);
+
 int cimpc_newton_create_ex(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q, const double* obj_u,
                            const double* obj_gamma, const double* obj_b, const double* obj_v, double kappa,
                            const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts) {
-  if (!ctx || H < 1 || H > 64 || R64 < 1 || R64 > (1 << 30) / H || !obj_q || !obj_u || !nopts || !ip_opts)
+  if (!obj_q) return CIMPC_ERR_INVALID_ARGUMENT;
+  return newton_create_impl(ctx, H, R64, obj_q, nullptr, obj_u, obj_gamma, obj_b, obj_v, nullptr, kappa, nopts, ip_opts);
+}
+
+int cimpc_newton_create_dense(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q_dense, const double* obj_u,
+                              const double* obj_v, const double* v_target, double kappa, const cimpc_newton_opts* nopts,
+                              const cimpc_ip_opts* ip_opts) {
+  if (!obj_q_dense) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (ctx && ctx->entry->desc.mode != 0) return CIMPC_ERR_UNSUPPORTED_MODEL;  // :configuration mode only
+  return newton_create_impl(ctx, H, R64, nullptr, obj_q_dense, obj_u, nullptr, nullptr, obj_v, v_target, kappa, nopts,
+                            ip_opts);
+}
+
+static int newton_create_impl(cimpc_ctx* ctx, int32_t H, int64_t R64, const double* obj_q, const double* obj_qd,
+                              const double* obj_u, const double* obj_gamma, const double* obj_b, const double* obj_v,
+                              const double* v_target, double kappa, const cimpc_newton_opts* nopts,
+                              const cimpc_ip_opts* ip_opts) {
+  if (!ctx || H < 1 || H > 64 || R64 < 1 || R64 > (1 << 30) / H || (!obj_q && !obj_qd) || !obj_u || !nopts || !ip_opts)
     return CIMPC_ERR_INVALID_ARGUMENT;
   if (!ctx->lin) return CIMPC_ERR_NOT_INITIALIZED;
   const LinLayout& l = ctx->entry->lay;
   const cimpc_model_desc& d = ctx->entry->desc;
   const int R = (int)R64, nq = d.nq, nu = d.nu, nw_ = d.nw, nd = l.nd, nth = l.nth, nz = l.nz, ncol = l.ncol;
   const int nyd = nd - nq;
-  // kernel variant
-  int variant = (d.mode == 0 && !obj_v) ? -1 : (obj_v ? 1 : 0);
+  // kernel variant: −1 specialised (:configuration, TrackingObjective), 0 / 1 general without / with velocity cost,
+  // 2 / 3 dense weights without / with velocity cost
+  int variant = obj_qd ? (obj_v ? 3 : 2) : ((d.mode == 0 && !obj_v) ? -1 : (obj_v ? 1 : 0));
   double wmin = 1e300;
-  for (int e = 0; e < H * nq; ++e) wmin = obj_q[e] < wmin ? obj_q[e] : wmin;
+  std::vector<double> h_e;
+  if (obj_qd) {
+    h_e.resize((size_t)H * nq * nq);
+    for (int t = 0; t < H; ++t)
+      if (!whitening_factor(nq, obj_qd + (size_t)t * nq * nq, h_e.data() + (size_t)t * nq * nq))
+        return CIMPC_ERR_INVALID_ARGUMENT;  // obj.q[t] must be symmetric positive definite (dual Schur form)
+  } else {
+    for (int e = 0; e < H * nq; ++e) wmin = obj_q[e] < wmin ? obj_q[e] : wmin;
+  }
   for (int e = 0; e < H * nu; ++e) wmin = obj_u[e] < wmin ? obj_u[e] : wmin;
   if (!(wmin > 0.0)) return CIMPC_ERR_INVALID_ARGUMENT;  // Q must be positive (dual Schur form)
   if (obj_v)
@@ -845,7 +907,8 @@ int cimpc_newton_create_ex(cimpc_ctx* ctx, int32_t H, int64_t R64, const double*
   newton_release(ctx);
   nw.variant = variant;
   const size_t n = (size_t)H * R;
-  const size_t lsc = variant < 0 ? ctx->entry->newton_scratch(H) : ctx->entry->newton_scratch_g[variant](H);
+  const size_t lsc = variant < 0 ? ctx->entry->newton_scratch(H)
+                     : (variant < 2 ? ctx->entry->newton_scratch_g[variant](H) : ctx->entry->newton_scratch_d[variant - 2](H));
   // carve one arena
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
@@ -866,6 +929,9 @@ int cimpc_newton_create_ex(cimpc_ctx* ctx, int32_t H, int64_t R64, const double*
                o_ty = take(sizeof(double) * R * H * (nyd > 0 ? nyd : 1)), o_cy = take(sizeof(double) * R * H * (nyd > 0 ? nyd : 1)),
                o_ry = take(sizeof(double) * H * (nyd > 0 ? nyd : 1)), o_oy = take(sizeof(double) * H * (nyd > 0 ? nyd : 1)),
                o_ov = take(sizeof(double) * H * nq),
+               o_qd = take(sizeof(double) * (obj_qd ? (size_t)H * nq * nq : 1)),
+               o_qe = take(sizeof(double) * (obj_qd ? (size_t)H * nq * nq : 1)),
+               o_qt = take(sizeof(double) * H * nq), o_vt = take(sizeof(double) * H * nq),
                o_lsc = take(sizeof(double) * R * lsc);
   CK(cudaMalloc(&nw.arena, off));
   CK(cudaMemset(nw.arena, 0, off));
@@ -902,8 +968,24 @@ int cimpc_newton_create_ex(cimpc_ctx* ctx, int32_t H, int64_t R64, const double*
   }
   nw.lscratch = (double*)(b + o_lsc);
   p.kappa = kappa; p.r_tol = nopts->r_tol; p.beta_init = nopts->beta_init; p.max_iter = nopts->max_iter;
-  CK(cudaMemcpy(nw.obj_q, obj_q, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
+  if (obj_q) CK(cudaMemcpy(nw.obj_q, obj_q, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(nw.obj_u, obj_u, sizeof(double) * H * nu, cudaMemcpyHostToDevice));
+  if (obj_qd) {
+    p.obj_qd = (double*)(b + o_qd); p.obj_e = (double*)(b + o_qe);
+    CK(cudaMemcpy((void*)p.obj_qd, obj_qd, sizeof(double) * (size_t)H * nq * nq, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((void*)p.obj_e, h_e.data(), sizeof(double) * (size_t)H * nq * nq, cudaMemcpyHostToDevice));
+    bool any_vt = false;
+    if (v_target)
+      for (int e = 0; e < H * nq; ++e) any_vt = any_vt || v_target[e] != 0.0;
+    if (any_vt) {  // q_target[t] = Σ_{s<t} v_target[s]  (objective.jl:36-44)
+      std::vector<double> qt((size_t)H * nq, 0.0);
+      for (int t = 1; t < H; ++t)
+        for (int k = 0; k < nq; ++k) qt[(size_t)t * nq + k] = qt[(size_t)(t - 1) * nq + k] + v_target[(size_t)(t - 1) * nq + k];
+      p.q_tgt = (double*)(b + o_qt); p.v_tgt = (double*)(b + o_vt);
+      CK(cudaMemcpy((void*)p.q_tgt, qt.data(), sizeof(double) * H * nq, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy((void*)p.v_tgt, v_target, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
+    }
+  }
   if (!nw.h_active) CK(cudaMallocHost(&nw.h_active, sizeof(int)));
   nw.ip = *ip_opts;
   nw.ip.diff_sol = 1;

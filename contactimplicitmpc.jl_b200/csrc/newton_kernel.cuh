@@ -84,6 +84,11 @@ struct NewtonParams {
   const double* ref_y = nullptr;                // H×nyd   `ref_traj.γ`, `ref_traj.b`
   const double* obj_y = nullptr;                // H×nyd   diagonals of obj.γ, obj.b
   const double* obj_v = nullptr;                // H×nq    diagonals of obj.v (null: TrackingObjective)
+  // dense-weight variant only (newton_dense.cuh)
+  const double* obj_qd = nullptr;               // H×nq×nq column-major  obj.q[t]
+  const double* obj_e = nullptr;                // H×nq×nq column-major  E_t = L_t⁻ᵀ, obj.q[t] = L_t L_tᵀ
+  const double* q_tgt = nullptr;                // H×nq    obj.q_target (null: zeros)
+  const double* v_tgt = nullptr;                // H×nq    obj.v_target (null: zeros)
 };
 
 template <class D>

@@ -8,6 +8,7 @@
 #include "lin_kernel.cuh"
 #include "newton_kernel.cuh"
 #include "newton_general.cuh"
+#include "newton_dense.cuh"
 #include "sim_kernel.cuh"
 
 namespace cimpc {
@@ -32,6 +33,9 @@ struct ModelEntry {
   // general device Newton (both modes; [0] TrackingObjective, [1] TrackingVelocityObjective)
   cudaError_t (*newton_step_g[2])(const NewtonParams& p, double* lscratch, cudaStream_t s);
   size_t (*newton_scratch_g[2])(int H);
+  // dense-weight device Newton (:configuration instances only; [0] without / [1] with velocity cost)
+  cudaError_t (*newton_step_d[2])(const NewtonParams& p, double* lscratch, cudaStream_t s);
+  size_t (*newton_scratch_d[2])(int H);
   // simulator step (generated residual of this robot)
   cudaError_t (*sim_step)(const SimParams& p, cudaStream_t s);
   size_t (*sim_scratch)(int R);  // doubles
@@ -86,6 +90,21 @@ cudaError_t launch_newton_step_general(const NewtonParams& p, double* lscratch, 
   const int grid = (p.R + NEWTON_WARPS - 1) / NEWTON_WARPS;
   newton_step_general_kernel<D, VEL, NEWTON_THREADS><<<grid, NEWTON_THREADS, bytes, s>>>(p, lscratch);
   return cudaGetLastError();
+}
+
+template <class D, bool VEL>
+cudaError_t launch_newton_step_dense(const NewtonParams& p, double* lscratch, cudaStream_t s) {
+  const size_t bytes = (size_t)NewtonDSmem<D, VEL>::per_warp(p.H) * NEWTON_WARPS * sizeof(double);
+  static SmemOptIn opt;
+  if (cudaError_t e = opt.ensure(newton_step_dense_kernel<D, VEL, NEWTON_THREADS>, bytes); e != cudaSuccess) return e;
+  const int grid = (p.R + NEWTON_WARPS - 1) / NEWTON_WARPS;
+  newton_step_dense_kernel<D, VEL, NEWTON_THREADS><<<grid, NEWTON_THREADS, bytes, s>>>(p, lscratch);
+  return cudaGetLastError();
+}
+
+template <class D, bool VEL>
+size_t newton_scratch_dense_doubles(int H) {
+  return NewtonDSmem<D, VEL>::l_doubles(H);
 }
 
 template <class D, bool VEL>
@@ -190,11 +209,14 @@ CIMPC_FOR_EACH_MODEL(CIMPC_DECLARE_ENTRY)
          &launch_newton_reset<D0>, &launch_newton_step<D0>, &newton_scratch_doubles<D0>,          \
          {&launch_newton_step_general<D0, false>, &launch_newton_step_general<D0, true>},         \
          {&newton_scratch_general_doubles<D0, false>, &newton_scratch_general_doubles<D0, true>}, \
+         {&launch_newton_step_dense<D0, false>, &launch_newton_step_dense<D0, true>},             \
+         {&newton_scratch_dense_doubles<D0, false>, &newton_scratch_dense_doubles<D0, true>},     \
          &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>, &launch_linearize<GEN>},               \
         {#name_, {nq, nu, nw, nc, nb, 1}, layout_of<D1>(), &launch_ip<D1>, &occupancy_ip<D1>,     \
          &launch_newton_reset<D1>, nullptr, nullptr,                                              \
          {&launch_newton_step_general<D1, false>, &launch_newton_step_general<D1, true>},         \
          {&newton_scratch_general_doubles<D1, false>, &newton_scratch_general_doubles<D1, true>}, \
+         {nullptr, nullptr}, {nullptr, nullptr},                                                  \
          &launch_sim_step<GEN>, &sim_scratch_doubles<GEN>, &launch_linearize<GEN>}};              \
     *count = 2;                                                                                   \
     return e;                                                                                     \

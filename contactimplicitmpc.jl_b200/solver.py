@@ -222,23 +222,38 @@ class Newton:
 
     def __init__(self, im_traj: ImplicitTrajectory, H_mpc: int, n_rollouts: int, obj_q, obj_u, kappa: float,
                  opts: NewtonOptions | None = None, ip_opts: InteriorPointOptions | None = None, *,
-                 obj_gamma=None, obj_b=None, obj_v=None):
+                 obj_gamma=None, obj_b=None, obj_v=None, v_target=None):
         """obj_gamma (H, nc), obj_b (H, nb): diagonals of obj.γ, obj.b — required for mode='configurationforce' (must
         be numerically zero, as in every example of the reference); obj_v (H, nq): velocity weights of a
-        `TrackingVelocityObjective` (objective.jl:18-47) or None."""
+        `TrackingVelocityObjective` (objective.jl:18-47) or None.
+        obj_q may also be (H, nq, nq): full symmetric positive definite matrices per stage (`relative_state_cost`,
+        centroidal_quadruped/model.jl:168-183), with v_target (H, nq) the velocity targets (objective.jl:34-46) —
+        the dense-weight kernel, mode='configuration' only."""
         self.im = im_traj
         self.H, self.R = int(H_mpc), int(n_rollouts)
         self.opts = opts or NewtonOptions()
         self.ip_opts = ip_opts or im_traj.opts
         self.force = im_traj.mode == "configurationforce"
-        oq = _f64(obj_q, (self.H, im_traj.nq))
         ou = _f64(obj_u, (self.H, im_traj.nu))
+        co, ci = self.opts.to_c(), self.ip_opts.to_c()
+        if np.ndim(obj_q) == 3:
+            oq = _f64(obj_q, (self.H, im_traj.nq, im_traj.nq))
+            if np.abs(oq - np.transpose(oq, (0, 2, 1))).max() > 1e-12 * max(1.0, np.abs(oq).max()):
+                raise ValueError("dense obj_q must be symmetric")
+            ov = _f64(obj_v, (self.H, im_traj.nq)) if obj_v is not None else None
+            vt = _f64(v_target, (self.H, im_traj.nq)) if v_target is not None else None
+            capi.check(im_traj._ctx, im_traj.lib.cimpc_newton_create_dense(
+                im_traj._ctx, self.H, self.R, oq.ctypes.data, ou.ctypes.data, ov.ctypes.data if ov is not None else None,
+                vt.ctypes.data if vt is not None else None, float(kappa), C.byref(co), C.byref(ci)))
+            return
+        if v_target is not None and np.any(np.asarray(v_target) != 0.0):
+            raise ValueError("v_target needs the dense-weight form of obj_q (pass np.stack([np.diag(q_t) ...]))")
+        oq = _f64(obj_q, (self.H, im_traj.nq))
         og = _f64(obj_gamma, (self.H, im_traj.nc)) if obj_gamma is not None else None
         ob = _f64(obj_b, (self.H, im_traj.nb)) if obj_b is not None else None
         ov = _f64(obj_v, (self.H, im_traj.nq)) if obj_v is not None else None
         if self.force and (og is None or ob is None):
             raise ValueError("mode='configurationforce' needs obj_gamma and obj_b")
-        co, ci = self.opts.to_c(), self.ip_opts.to_c()
         capi.check(im_traj._ctx, im_traj.lib.cimpc_newton_create_ex(
             im_traj._ctx, self.H, self.R, oq.ctypes.data, ou.ctypes.data,
             og.ctypes.data if og is not None else None, ob.ctypes.data if ob is not None else None,

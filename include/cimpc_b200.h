@@ -257,6 +257,20 @@ int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n_rollouts, const double* q0
 int cimpc_newton_create_ex(cimpc_ctx* ctx, int32_t H_mpc, int64_t n_rollouts, const double* obj_q, const double* obj_u,
                            const double* obj_gamma, const double* obj_b, const double* obj_v, double kappa,
                            const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts);
+/*
+ * DENSE configuration weights and velocity targets — `Newton(...; obj)` with per-stage full matrices `obj.q[t]`, e.g.
+ * `relative_state_cost(q_body, q_orientation, q_foot)` (src/dynamics/centroidal_quadruped/model.jl:168-183) as used by
+ * examples/centroidal_quadruped/flat_trot.jl:37-42, and a `TrackingVelocityObjective` with `v_target`
+ * (src/controller/objective.jl:18-47; `q_target` is accumulated from it as in :36-44).  :configuration mode.
+ *   obj_q_dense nq × nq × H_mpc  HOST, column-major, symmetric positive definite (else CIMPC_ERR_INVALID_ARGUMENT)
+ *   obj_v       nq × H_mpc       diagonals of `obj.v[t]`, or NULL for a `TrackingObjective`
+ *   v_target    nq × H_mpc       `obj.v_target[t]`, or NULL for zeros
+ * Solved by cimpc_newton_solve_batch / _ex / _ex2 / _host like the other variants (csrc/newton_dense.cuh: the
+ * configuration block is whitened with the Cholesky factor of `obj.q[t]`; the direction equals `R \ r` to round-off).
+ */
+int cimpc_newton_create_dense(cimpc_ctx* ctx, int32_t H_mpc, int64_t n_rollouts, const double* obj_q_dense,
+                              const double* obj_u, const double* obj_v, const double* v_target, double kappa,
+                              const cimpc_newton_opts* nopts, const cimpc_ip_opts* ip_opts);
 int cimpc_newton_solve_batch_ex(cimpc_ctx* ctx, const int32_t* window, const double* ref_q, const double* ref_u,
                                 const double* ref_gamma, const double* ref_b, double mu, double h, const double* q0,
                                 const double* q1, const uint8_t* active, int32_t warm_start, double* u_out,

@@ -33,12 +33,29 @@ class NewtonOptions:  # newton.jl:2-11
 @dataclass
 class TrackingObjective:
     """`TrackingObjective` (objective.jl:3-16) and, when `v` is given, `TrackingVelocityObjective`
-    (objective.jl:18-47) with zero `v_target` / `q_target` — diagonal weights per stage."""
-    q: np.ndarray  # (H, nq)
+    (objective.jl:18-47).  `q` holds per-stage diagonals (H, nq) or full matrices (H, nq, nq) — e.g.
+    `relative_state_cost` (src/dynamics/centroidal_quadruped/model.jl:168-183); `v_target` (H, nq) as in
+    objective.jl:34-46, from which `q_target` is accumulated."""
+    q: np.ndarray  # (H, nq) or (H, nq, nq)
     u: np.ndarray  # (H, nu)
     gamma: np.ndarray  # (H, nc)
     b: np.ndarray  # (H, nb)
     v: np.ndarray | None = None  # (H, nq) velocity weights
+    v_target: np.ndarray | None = None  # (H, nq)
+
+    def __post_init__(self):
+        self.q_target = None
+        if self.v_target is not None and np.any(self.v_target != 0.0):  # objective.jl:36-44
+            qt = np.zeros_like(self.v_target)
+            for t in range(1, len(qt)):
+                qt[t] = qt[t - 1] + self.v_target[t - 1]
+            self.q_target = qt
+
+    def q_mul(self, t, x):
+        return self.q[t] @ x if self.q[t].ndim == 2 else self.q[t] * x
+
+    def q_mat(self, t):
+        return self.q[t] if self.q[t].ndim == 2 else np.diag(self.q[t])
 
 
 class NewtonLayout:
@@ -110,13 +127,16 @@ class Newton:
         d, dq0, dq1, du1 = dyn_out
         r = np.zeros(L.n)
         for t in range(H):
-            r[L.pr(t, L.iq)] += self.obj.q[t] * (traj.q[t + 2] - ref.q[t + 2])
+            qt = 0.0 if self.obj.q_target is None else self.obj.q_target[t]  # newton_residual.jl:229, 262
+            r[L.pr(t, L.iq)] += self.obj.q_mul(t, traj.q[t + 2] - (ref.q[t + 2] + qt))
             r[L.pr(t, L.iu)] += self.obj.u[t] * (traj.u[t] - ref.u[t])
             if self.mode == "configurationforce":
                 r[L.pr(t, L.ig)] += self.obj.gamma[t] * (traj.gamma[t] - ref.gamma[t])
                 r[L.pr(t, L.ib)] += self.obj.b[t] * (traj.b[t] - ref.b[t])
             if self.obj.v is not None:  # gradient!(…, ::TrackingVelocityObjective)  newton_residual.jl:221-281
                 dv = self.obj.v[t] * (traj.q[t + 2] - traj.q[t + 1])
+                if self.obj.v_target is not None and self.mode == "configuration":
+                    dv = dv - self.obj.v[t] * self.obj.v_target[t]  # only the :configuration method has it (:270, :276)
                 r[L.pr(t, L.iq)] += dv
                 if t >= 1:
                     r[L.pr(t - 1, L.iq)] -= dv
@@ -136,7 +156,7 @@ class Newton:
         _, dq0, dq1, du1 = dyn_out
         R = np.zeros((L.n, L.n))
         for t in range(H):
-            R[L.pr(t, L.iq), L.pr(t, L.iq)] += self.obj.q[t]
+            R[np.ix_(L.pr(t, L.iq), L.pr(t, L.iq))] += self.obj.q_mat(t)
             R[L.pr(t, L.iu), L.pr(t, L.iu)] += self.obj.u[t]
             if self.mode == "configurationforce":
                 R[L.pr(t, L.ig), L.pr(t, L.ig)] += self.obj.gamma[t]

@@ -261,6 +261,94 @@ def test_general_newton_matches_oracle(cuda_device, robot, mode, vel):
     assert worst <= (2e-5 if robot == "flamingo" else 1e-6), worst
 
 
+def relative_state_cost(qbody, qorientation, qfoot):
+    """src/dynamics/centroidal_quadruped/model.jl:168-183, restated: ½ bodyᵀQb body + ½ oriᵀQo ori + Σ ½ (foot − body)ᵀ Qf (foot − body)."""
+    Q = np.zeros((18, 18))
+    Q[0:3, 0:3] = np.diag(qbody)
+    Q[3:6, 3:6] = np.diag(qorientation)
+    for i in range(1, 5):
+        f = slice(3 + 3 * i, 6 + 3 * i)
+        Q[0:3, 0:3] += np.diag(qfoot)
+        Q[f, f] += np.diag(qfoot)
+        Q[0:3, f] += -np.diag(qfoot)
+        Q[f, 0:3] += -np.diag(qfoot)
+    return Q
+
+
+@pytest.mark.parametrize("case", ["flat_trot", "flat_trot_v_target", "dense_no_velocity", "diagonal_as_dense"])
+def test_dense_weight_newton_matches_oracle(cuda_device, case):
+    """The REAL objective of examples/centroidal_quadruped/flat_trot.jl:37-42 (BASELINE config 5's robot):
+    `TrackingVelocityObjective` with q = relative_state_cost(1e-0·[1e-2, 1e-2, 1], 3e-1·[1, 1, 1], 1e-0·[0.2, 0.2, 1]) — a
+    NON-diagonal matrix coupling the body position with every foot —, v = 1e-3·[1 1 1; 1e3·[1 1 1]; 1 …], u = 3e-3, and
+    v_target (zero in the example since v0 = 0; a non-zero target is exercised as well), H_mpc = 10, κ_mpc = 2e-4, IP
+    r_tol 1e-4 / κ_tol κ_mpc / undercut 5, Newton r_tol 3e-5 / max_iter 5 — device dense-weight kernel vs the oracle's
+    dense KKT solve.  `diagonal_as_dense` feeds a diagonal objective through the dense kernel and must reproduce the
+    general (diagonal) kernel."""
+    import torch
+    import cimpc_b200 as cb
+    from oracle.newton import TrackingObjective
+    robot, mode, H, kappa = "centroidal_quadruped", "configuration", 10, 2.0e-4
+    m, lin, gait, ref = _reference_traj(robot)
+    nq = m.nq
+    Q = relative_state_cost(1e-0 * np.array([1e-2, 1e-2, 1]), 3e-1 * np.array([1.0, 1, 1]), 1e-0 * np.array([0.2, 0.2, 1]))
+    ov = np.tile(1e-3 * np.array([1.0, 1, 1, 1e3, 1e3, 1e3] + [1.0] * 12), (H, 1))
+    ou = np.tile(3e-3 * np.ones(m.nu), (H, 1))
+    vt = None
+    if case == "flat_trot_v_target":
+        v0 = 0.05 * gait["h"]  # flat_trot.jl:42 passes 1/h·[v0 …]-shaped targets; any (H, nq) array is legal
+        vt = np.tile(np.array([v0, 0, 0, 0, 0, 0] + [v0, 0, 0] * 4), (H, 1))
+    if case == "dense_no_velocity":
+        ov = None
+    if case == "diagonal_as_dense":
+        Q = np.diag(1e-1 * (0.5 + np.random.default_rng(2).random(nq)))
+    oq = np.tile(Q, (H, 1, 1))
+    og, ob = np.full((H, m.nc), 1e-100), np.full((H, m.nb), 1e-100)
+    obj = TrackingObjective(q=oq, u=ou, gamma=og, b=ob, v=ov, v_target=vt)
+    ip_kw = dict(r_tol=1e-4, kappa_tol=kappa, max_iter=100, max_ls=0, undercut=5.0)
+    n_opts = dict(r_tol=3e-5, max_iter=5)
+    R = 8
+    rng = np.random.default_rng(77)
+    q0 = np.tile(ref.q[0], (R, 1))
+    q1 = ref.q[1] + 0.003 * rng.standard_normal((R, nq))
+    q1[0] = ref.q[1]
+    window = np.arange(H + 2, dtype=np.int32)
+    im = cb.ImplicitTrajectory(*SIZES[robot], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"], mode=mode,
+                               opts=cb.InteriorPointOptions(diff_sol=True, **ip_kw))
+    nw = cb.Newton(im, H, R, oq, ou, kappa, cb.NewtonOptions(**n_opts), obj_v=ov, v_target=vt)
+    mu = float(lin["th0"][0, -2])
+    u, q, info = nw.solve(window, ref.q[:H + 2], ref.u[:H], mu, gait["h"], torch.from_numpy(q0).to(cuda_device),
+                          torch.from_numpy(q1).to(cuda_device), want_q=True)
+    torch.cuda.synchronize()
+    u, q, info = u.cpu().numpy(), q.cpu().numpy(), info.cpu().numpy()
+    assert info[:, 0].max() >= 1, "the test must exercise at least one Newton iteration"
+    agree, worst = 0, 0.0
+    for r in range(R):
+        core, dyn = _oracle_newton_general(robot, mode, m, lin, gait, H, obj, kappa, ip_kw, n_opts)
+        uo = core.solve(dyn, q0[r], q1[r], list(window), ref, warm_start=False)
+        if core.stats["iters"] == info[r, 0] and core.stats["ip_sweeps"] == info[r, 1]:
+            agree += 1
+            worst = max(worst, np.abs(u[r] - uo).max() / max(1.0, np.abs(uo).max()), np.abs(q[r] - core.traj.q).max())
+        conv = np.abs(core.res).sum() / len(core.res) < n_opts["r_tol"]
+        assert bool(info[r, 2]) == bool(conv)
+    assert agree >= R - 1, f"only {agree}/{R} rollouts followed the oracle's iteration path"
+    assert worst <= 1e-6, worst
+    if case == "diagonal_as_dense":
+        dq = np.tile(np.diag(Q), (H, 1))
+        im2 = cb.ImplicitTrajectory(*SIZES[robot], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"], mode=mode,
+                                    opts=cb.InteriorPointOptions(diff_sol=True, **ip_kw))
+        nw2 = cb.Newton(im2, H, R, dq, ou, kappa, cb.NewtonOptions(**n_opts), obj_v=ov)
+        u2, q2, info2 = nw2.solve(window, ref.q[:H + 2], ref.u[:H], mu, gait["h"], torch.from_numpy(q0).to(cuda_device),
+                                  torch.from_numpy(q1).to(cuda_device), want_q=True)
+        same = (info2.cpu().numpy()[:, :2] == info[:, :2]).all(axis=1)
+        assert same.mean() >= 0.85
+        assert np.abs(u2.cpu().numpy() - u)[same].max() <= 1e-8 and np.abs(q2.cpu().numpy() - q)[same].max() <= 1e-8
+    # a matrix that is not positive definite is refused
+    bad = oq.copy()
+    bad[3] = -bad[3]
+    with pytest.raises(cb.CimpcError):
+        cb.Newton(im, H, R, bad, ou, kappa, cb.NewtonOptions(**n_opts), obj_v=ov)
+
+
 def test_general_kernel_equals_specialised_kernel(cuda_device):
     """(:configuration, TrackingObjective) through the GENERAL kernel — selected by passing velocity weights of 1e-300,
     which change nothing numerically — reproduces the specialised kernel: same iteration / sweep counts, u and q to

@@ -16,7 +16,8 @@ def structured_solve(L, H, nq, nu, nyd, obj_q, obj_u, obj_v, dq0, dq1, du1, res,
     r_u = np.array([res[L.pr(t, L.iu)] for t in range(H)])
     r_x = np.array([res[L.pr(t, L.iq)] for t in range(H)])
     r_nu = np.array([res[L.du(t)] for t in range(H)])
-    Wq, Wu = 1.0 / obj_q, 1.0 / obj_u
+    Wu = 1.0 / obj_u
+    dense_q = obj_q.ndim == 3  # per-stage full matrices (relative_state_cost): P⁻¹ is block diagonal with Q_t⁻¹
     A, B, U = dq1[:, :nq, :], dq0[:, :nq, :], du1[:, :nq, :]
     dnu_y = np.zeros((H, nyd))
     if nyd:  # zero-weight (γ, b) rows: Δν^y = −r_y, its coupling moves to the right-hand side
@@ -43,13 +44,16 @@ def structured_solve(L, H, nq, nu, nyd, obj_q, obj_u, obj_v, dq0, dq1, du1, res,
             C[r0 + nq:r0 + nb, t * npr + nu:(t + 1) * npr] = np.eye(nq)
             if t >= 1:
                 C[r0 + nq:r0 + nb, (t - 1) * npr + nu:t * npr] = -np.eye(nq)
-    W = np.concatenate([np.concatenate([Wu[t], Wq[t]]) for t in range(H)])
+    W = np.zeros((H * npr, H * npr))
+    for t in range(H):
+        W[t * npr:t * npr + nu, t * npr:t * npr + nu] = np.diag(Wu[t])
+        W[t * npr + nu:(t + 1) * npr, t * npr + nu:(t + 1) * npr] = np.linalg.inv(obj_q[t]) if dense_q else np.diag(1.0 / obj_q[t])
     reg = np.zeros(n)
     for t in range(H):
         reg[t * nb:t * nb + nq] = rho
         if vel:
             reg[t * nb + nq:(t + 1) * nb] = 1.0 / obj_v[t]
-    Y = (C * W) @ C.T + np.diag(reg)
+    Y = C @ W @ C.T + np.diag(reg)
     # block-pentadiagonal: nothing outside the band of three stage blocks
     for t1 in range(H):
         for t2 in range(H):
@@ -59,9 +63,9 @@ def structured_solve(L, H, nq, nu, nyd, obj_q, obj_u, obj_v, dq0, dq1, du1, res,
     rd = np.zeros(n)
     for t in range(H):
         rd[t * nb:t * nb + nq] = r_nu[t][:nq]
-    dmu = np.linalg.solve(Y, C @ (W * rp) - rd)
+    dmu = np.linalg.solve(Y, C @ (W @ rp) - rd)
     np.linalg.cholesky(Y)  # SPD: the kernel factorises it without pivoting
-    dp = W * (rp - C.T @ dmu)
+    dp = W @ (rp - C.T @ dmu)
     delta = np.zeros(L.n)
     for t in range(H):
         delta[L.pr(t, L.iu)] = dp[t * npr:t * npr + nu]
@@ -79,9 +83,10 @@ def structured_solve(L, H, nq, nu, nyd, obj_q, obj_u, obj_v, dq0, dq1, du1, res,
     return delta
 
 
-@pytest.mark.parametrize("robot,mode,vel", [("quadruped", "configuration", False), ("quadruped", "configuration", True),
-                                            ("flamingo", "configurationforce", False), ("flamingo", "configurationforce", True)])
-def test_augmented_dual_schur_equals_dense_kkt(robot, mode, vel):
+@pytest.mark.parametrize("robot,mode,vel,dense", [("quadruped", "configuration", False, False), ("quadruped", "configuration", True, False),
+                                                  ("flamingo", "configurationforce", False, False), ("flamingo", "configurationforce", True, False),
+                                                  ("quadruped", "configuration", False, True), ("quadruped", "configuration", True, True)])
+def test_augmented_dual_schur_equals_dense_kkt(robot, mode, vel, dense):
     from oracle.c_oracle import COracle
     from oracle.ip import IPOptions
     from oracle.models import get_model
@@ -112,6 +117,15 @@ def test_augmented_dual_schur_equals_dense_kkt(robot, mode, vel):
     obj = TrackingObjective(q=np.tile(0.1 * (0.5 + rng.random(nq)), (H, 1)), u=np.tile(0.3 * (0.5 + rng.random(nu)), (H, 1)),
                             gamma=np.full((H, nc), 1e-100), b=np.full((H, nb_), 1e-100),
                             v=np.tile(1e-3 * (1 + 100 * rng.random(nq)), (H, 1)) if vel else None)
+    if dense:  # a full SPD weight per stage and a velocity target (objective.jl:34-46)
+        Qs = []
+        for t in range(H):
+            Mq = rng.standard_normal((nq, nq))
+            Qs.append(0.05 * (Mq @ Mq.T / nq + np.diag(0.5 + rng.random(nq))))
+        obj.q = np.array(Qs)
+        if vel:
+            obj.v_target = 0.01 * rng.standard_normal((H, nq))
+            obj.__post_init__()
     nw = Newton(m, H, gait["h"], obj, kappa, NewtonOptions(r_tol=3e-4, max_iter=5), mode=mode)
     nw.reset(ref, ref.q[0], ref.q[1] + 0.01 * rng.standard_normal(nq), False)
     nw.nu_[:] = 0.01 * rng.standard_normal(nw.nu_.shape)  # non-trivial duals, force duals included
