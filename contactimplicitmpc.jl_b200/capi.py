@@ -21,7 +21,7 @@ SYMBOLS = [
     "cimpc_newton_opts_default", "cimpc_newton_create", "cimpc_newton_solve_batch", "cimpc_newton_last_sweeps",
     "cimpc_sim_step_batch", "cimpc_linearize", "cimpc_get_linearization",
     "cimpc_newton_create_ex", "cimpc_newton_solve_batch_ex", "cimpc_newton_solve_batch_ex2",
-    "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex", "cimpc_newton_create_dense",
+    "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex", "cimpc_newton_create_dense", "cimpc_create_named",
 ]
 
 
@@ -76,6 +76,8 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_version.restype = C.c_int
     lib.cimpc_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(ModelDesc)]
     lib.cimpc_create.restype = C.c_int
+    lib.cimpc_create_named.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(ModelDesc), C.c_char_p]
+    lib.cimpc_create_named.restype = C.c_int
     lib.cimpc_destroy.argtypes = [vp]
     lib.cimpc_destroy.restype = C.c_int
     lib.cimpc_get_dims.argtypes = [vp, C.POINTER(Dims)]

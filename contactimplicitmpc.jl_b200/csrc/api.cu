@@ -375,13 +375,21 @@ static void newton_release(cimpc_ctx* ctx) {
   nw.ready = false;
 }
 
-static const ModelEntry* find_entry(const cimpc_model_desc& d) {
-#define CIMPC_SEARCH(name, nq, nu, nw, nc, nb)                                                   \
+// First compiled instance with these sizes / mode (the nominal robots come first); with a name, the instance of that
+// model — the reference's names (`get_simulation("centroidal_quadruped", …)`, `model_variable_name = "quadruped_payload"`)
+// and the short tags of csrc/gen are both accepted.
+static const ModelEntry* find_entry(const cimpc_model_desc& d, const char* model_name) {
+  std::string want = model_name ? model_name : "";
+  if (want == "hopper_2D") want = "hopper2d";
+  if (want == "centroidal_quadruped") want = "centroidal";
+  if (want == "centroidal_quadruped_payload") want = "centroidal_payload";
+#define CIMPC_SEARCH(tag_, nq, nu, nw, nc, nb)                                                   \
   {                                                                                              \
     int cnt = 0;                                                                                 \
-    const ModelEntry* e = entries_##name(&cnt);                                                  \
+    const ModelEntry* e = entries_##tag_(&cnt);                                                  \
     for (int i = 0; i < cnt; ++i)                                                                \
-      if (std::memcmp(&e[i].desc, &d, sizeof(cimpc_model_desc)) == 0) return &e[i];              \
+      if (std::memcmp(&e[i].desc, &d, sizeof(cimpc_model_desc)) == 0 && (want.empty() || want == e[i].name))      \
+        return &e[i];                                                                            \
   }
   CIMPC_FOR_EACH_MODEL(CIMPC_SEARCH)
 #undef CIMPC_SEARCH
@@ -497,9 +505,13 @@ int cimpc_version(void) { return CIMPC_B200_VERSION; }
 int64_t cimpc_launch_count(const cimpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int cimpc_create(cimpc_ctx** out, int device, const cimpc_model_desc* desc) {
+  return cimpc_create_named(out, device, desc, nullptr);
+}
+
+int cimpc_create_named(cimpc_ctx** out, int device, const cimpc_model_desc* desc, const char* model_name) {
   if (!out || !desc) return CIMPC_ERR_INVALID_ARGUMENT;
   *out = nullptr;
-  const ModelEntry* e = find_entry(*desc);
+  const ModelEntry* e = find_entry(*desc, model_name);
   if (!e) return CIMPC_ERR_UNSUPPORTED_MODEL;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {

@@ -95,10 +95,14 @@ struct Dims {
 
 // The robots of BASELINE.json's configs (SURVEY.md §2 dimension table).
 //                         nq  nu nw nc nb
-#define CIMPC_FOR_EACH_MODEL(X) \
-  X(hopper2d, 4, 2, 2, 1, 2)    \
-  X(quadruped, 11, 8, 2, 4, 8)  \
-  X(flamingo, 9, 6, 2, 4, 8)    \
-  X(centroidal, 18, 12, 3, 4, 16)
+// The *_payload entries share the sizes (and therefore the solver kernels) of their nominal robot; what differs is the
+// generated residual used by the simulator step and the device linearization (cimpc_create_named selects them).
+#define CIMPC_FOR_EACH_MODEL(X)        \
+  X(hopper2d, 4, 2, 2, 1, 2)           \
+  X(quadruped, 11, 8, 2, 4, 8)         \
+  X(flamingo, 9, 6, 2, 4, 8)           \
+  X(centroidal, 18, 12, 3, 4, 16)      \
+  X(quadruped_payload, 11, 8, 2, 4, 8) \
+  X(centroidal_payload, 18, 12, 3, 4, 16)
 
 }  // namespace cimpc

@@ -43,7 +43,10 @@ else:
 
 GEN_DIR = os.path.join(os.path.dirname(HERE), "csrc", "gen")
 ROBOTS = {"hopper_2D": "hopper2d", "quadruped": "quadruped", "flamingo": "flamingo",
-          "centroidal_quadruped": "centroidal"}
+          "centroidal_quadruped": "centroidal",
+          # payload variants: same sizes and kernels, other inertial parameters (examples/quadruped/payload.jl simulates
+          # `quadruped_payload` under a policy built on the nominal model; BASELINE config 5 asks for the centroidal analogue)
+          "quadruped_payload": "quadruped_payload", "centroidal_quadruped_payload": "centroidal_payload"}
 
 
 class _Printer(C99CodePrinter):

@@ -421,4 +421,12 @@ def get_model(name: str) -> Model:
         return Flamingo()
     if name == "centroidal_quadruped":
         return CentroidalQuadruped()
+    if name == "centroidal_quadruped_payload":
+        # BASELINE config 5 ("centroidal_quadruped + payload").  The reference ships no centroidal payload model; this
+        # one carries the payload of `quadruped_payload` (src/dynamics/quadruped/model.jl:530-531: 3 kg, 0.03 kg m²) on
+        # the body: mass_body + 3.0, inertia_body + 0.03·I.
+        m = CentroidalQuadruped(mass_body=13.5 + 3.0, inertia=[0.0178533 * 10.0 + 0.03, 0.0377999 * 10.0 + 0.03,
+                                                                  0.0456542 * 10.0 + 0.03])
+        m.name = "centroidal_quadruped_payload"
+        return m
     raise KeyError(name)

@@ -59,7 +59,7 @@ class MonteCarloRollouts:
                  kappa, n_rollouts, newton_opts: NewtonOptions | None = None,
                  sim_opts: InteriorPointOptions | None = None, obj_gamma=None, obj_b=None, obj_v=None,
                  ref_gamma=None, ref_b=None, altitude_update: bool = False, altitude_impact_threshold: float = 1.0,
-                 **newton_kw):
+                 sim_model: str | None = None, **newton_kw):
         """obj_gamma / obj_b / ref_gamma / ref_b: required when `im_traj.mode == "configurationforce"`;
         obj_v: velocity weights of a TrackingVelocityObjective (the flamingo policy, examples/flamingo/flat.jl:34-41);
         altitude_update / altitude_impact_threshold: `CIMPCOptions` (src/controller/policy.jl:1-14) — every policy
@@ -72,8 +72,9 @@ class MonteCarloRollouts:
         self.newton = Newton(im_traj, H_mpc, n_rollouts, obj_q, obj_u, kappa, newton_opts, obj_gamma=obj_gamma,
                              obj_b=obj_b, obj_v=obj_v, **newton_kw)
         self.altitude_update, self.alt_threshold = bool(altitude_update), float(altitude_impact_threshold)
+        # sim_model: the simulated plant, e.g. "quadruped_payload" under a policy built on the nominal robot
         self.sim = Simulator(im_traj.nq, im_traj.nu, im_traj.nw, im_traj.nc, im_traj.nb, opts=sim_opts or simulator_options(),
-                             device=im_traj.device)
+                             device=im_traj.device, model=sim_model)
         self.mpc_steps = 0
 
     def run(self, q1, v1, H_sim, record_every: int = 1, dist=None):
@@ -159,24 +160,33 @@ class GroupedRollouts:
     during which most SMs idle — with several parts in flight another part's `newton_solve!` sweep or simulator step
     fills them.  Per-rollout arithmetic is unchanged (same kernels, same inputs).
 
-    make_im: () -> ImplicitTrajectory (one per part: the Newton state lives in the context);
-    mc_kwargs: the keyword arguments of MonteCarloRollouts except `n_rollouts`."""
+    make_im: () -> ImplicitTrajectory, or (g) -> ImplicitTrajectory (one per part: the Newton state lives in the context);
+    mc_kwargs: the keyword arguments of MonteCarloRollouts except `n_rollouts`;
+    group_kwargs: optional list (one dict per part) of overrides — a ROLLOUT GROUP may have its own simulated plant
+    (`sim_model="quadruped_payload"`, examples/quadruped/payload.jl), its own linearization (make_im(g) may linearize
+    another model or reference: `update!(lin, s, z, θ)`, linearized_step.jl:48-55) or objective.  This is how per-group
+    model variation (BASELINE config 5) runs: one context per group, groups concurrent on their own streams."""
 
-    def __init__(self, make_im, n_rollouts: int, groups: int, *mc_args, **mc_kwargs):
+    def __init__(self, make_im, n_rollouts: int, groups: int, *mc_args, group_kwargs=None, **mc_kwargs):
+        import inspect
         G = max(1, min(int(groups), int(n_rollouts)))
         base = [(n_rollouts * g) // G for g in range(G + 1)]
         self.bounds = [(base[g], base[g + 1]) for g in range(G)]
         self.parts = []
-        for lo, hi in self.bounds:
-            im = make_im()
-            self.parts.append(MonteCarloRollouts(im, *mc_args, n_rollouts=hi - lo, **mc_kwargs))
+        takes_g = len(inspect.signature(make_im).parameters) >= 1
+        for g, (lo, hi) in enumerate(self.bounds):
+            im = make_im(g) if takes_g else make_im()
+            kw = dict(mc_kwargs)
+            if group_kwargs is not None:
+                kw.update(group_kwargs[g])
+            self.parts.append(MonteCarloRollouts(im, *mc_args, n_rollouts=hi - lo, **kw))
         self.mpc_steps = 0
 
     @property
     def launch_count(self) -> int:
         return sum(p.im.launch_count for p in self.parts)
 
-    def run(self, q1, v1, H_sim, record_every: int = 1):
+    def run(self, q1, v1, H_sim, record_every: int = 1, dist=None):
         import threading
         import torch
         main = torch.cuda.current_stream(q1.device)
@@ -189,7 +199,7 @@ class GroupedRollouts:
                 torch.cuda.set_device(q1.device)
                 streams[g].wait_stream(main)
                 with torch.cuda.stream(streams[g]):
-                    outs[g] = self.parts[g].run(q1[lo:hi].contiguous(), v1[lo:hi].contiguous(), H_sim, record_every)
+                    outs[g] = self.parts[g].run(q1[lo:hi].contiguous(), v1[lo:hi].contiguous(), H_sim, record_every, dist=dist)
             except BaseException as e:  # re-raised in the caller's thread
                 errs[g] = e
 

@@ -97,6 +97,15 @@ int cimpc_version(void);
  * one context holds what the reference spreads over `im_traj.ip[1:H_ref]`.
  */
 int cimpc_create(cimpc_ctx** ctx, int device, const cimpc_model_desc* desc);
+/*
+ * Same, selecting the robot MODEL by name among the compiled instances of these sizes — `get_simulation(model_name, …;
+ * model_variable_name = …)` of the reference (src/simulation/simulation.jl, examples/quadruped/payload.jl:10-14):
+ * "hopper_2D", "quadruped", "flamingo", "centroidal_quadruped", and the payload variants "quadruped_payload"
+ * (src/dynamics/quadruped/model.jl:530-582: torso mass + 3 kg, inertia + 0.03) and "centroidal_quadruped_payload" (the
+ * same payload on the centroidal body; the reference ships no such model).  The name only matters for the entry
+ * points that evaluate the robot's generated residual (cimpc_sim_step_batch*, cimpc_linearize); NULL = cimpc_create.
+ */
+int cimpc_create_named(cimpc_ctx** ctx, int device, const cimpc_model_desc* desc, const char* model_name);
 int cimpc_destroy(cimpc_ctx* ctx);
 int cimpc_get_dims(const cimpc_ctx* ctx, cimpc_dims* dims);
 

@@ -418,4 +418,9 @@ def get_model(name: str) -> Model:
         return Flamingo()
     if name == "centroidal_quadruped":
         return CentroidalQuadruped()
+    if name == "centroidal_quadruped_payload":  # no reference counterpart: quadruped_payload's 3 kg / 0.03 kg m² on the body
+        m = CentroidalQuadruped(mass_body=13.5 + 3.0, inertia=[0.0178533 * 10.0 + 0.03, 0.0377999 * 10.0 + 0.03,
+                                                                  0.0456542 * 10.0 + 0.03])
+        m.name = "centroidal_quadruped_payload"
+        return m
     raise KeyError(name)

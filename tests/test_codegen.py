@@ -33,7 +33,8 @@ void rth_eval(const double* z, const double* th, double* J) {
 
 
 @pytest.mark.parametrize("robot,tag", [("hopper_2D", "hopper2d"), ("quadruped", "quadruped"), ("flamingo", "flamingo"),
-                                       ("centroidal_quadruped", "centroidal")])
+                                       ("centroidal_quadruped", "centroidal"), ("quadruped_payload", "quadruped_payload"),
+                                       ("centroidal_quadruped_payload", "centroidal_payload")])
 def test_generated_residual_matches_oracle(tmp_path, robot, tag):
     from oracle.residual import get_residual
     hdr = os.path.join(GEN, f"residual_{tag}.h")
@@ -45,7 +46,8 @@ def test_generated_residual_matches_oracle(tmp_path, robot, tag):
     lib = C.CDLL(str(so))
     res = get_residual(robot)
     nz, nth = res.idx.nz, res.idx.ntheta
-    assert (nz, nth) == (SIZES[robot][0] + 4 * SIZES[robot][3] + 2 * SIZES[robot][4], nth)
+    base = robot.replace("_payload", "")
+    assert (nz, nth) == (SIZES[base][0] + 4 * SIZES[base][3] + 2 * SIZES[base][4], nth)
     nnz = lib.nnz()
     row = np.zeros(nnz, np.int32); col = np.zeros(nnz, np.int32)
     lib.pattern(row.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p))

@@ -160,6 +160,44 @@ def test_altitude_update_and_disturbances_in_the_loop(cuda_device):
     assert np.abs(a["q"][25] - b["q"][25]).max() > 1e-4
 
 
+def test_payload_plant_under_nominal_policy_in_rollout_groups(cuda_device):
+    """examples/quadruped/payload.jl: the policy is built on the nominal quadruped, the simulated plant carries the
+    payload (`quadruped_payload`: + 3 kg, + 0.03 kg m² on the torso).  Two rollout GROUPS in one run — nominal plant and
+    payload plant — each with its own context (`GroupedRollouts(group_kwargs=…)`): the nominal group reproduces the
+    plain run bit for bit, the payload group stays on the gait (the reference's claim for this example) with a visibly
+    different trajectory and larger normal forces."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait, load_lin
+    robot = "quadruped"
+    lin, gait = load_lin(robot), load_gait(robot)
+    nq, nu = SIZES[robot][0], SIZES[robot][1]
+    R, N, H_sim = 8, 5, 300
+    opts = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=1e-4, undercut=5.0, diff_sol=True)
+    oq = np.tile(1e-2 * np.array([10.0, 0.02, 0.25] + [0.5] * (nq - 3)), (H_MPC, 1))   # payload.jl:36-40
+    ou = np.tile(3e-2 * np.ones(nu), (H_MPC, 1))
+
+    def make_im():
+        return cb.ImplicitTrajectory(*SIZES[robot], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
+                                     mode="configuration", opts=opts)
+    q1 = torch.from_numpy(np.tile(gait["q"][1], (R, 1))).to(cuda_device)
+    v1 = torch.from_numpy(np.tile((gait["q"][1] - gait["q"][0]) / gait["h"], (R, 1))).to(cuda_device)
+    kw = dict(H_mpc=H_MPC, N_sample=N, obj_q=oq, obj_u=ou, kappa=1e-4, newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5),
+              altitude_update=True, altitude_impact_threshold=0.05)                     # payload.jl:48-53
+    mc = cb.GroupedRollouts(make_im, R, 2, gait["q"], gait["u"], gait["mu"], 1.0, gait["h"],
+                            group_kwargs=[dict(), dict(sim_model="quadruped_payload")], **kw)
+    out = {k: v.cpu().numpy() for k, v in mc.run(q1, v1, H_sim).items()}
+    plain = cb.MonteCarloRollouts(make_im(), gait["q"], gait["u"], gait["mu"], 1.0, gait["h"], n_rollouts=R // 2, **kw)
+    ref = {k: v.cpu().numpy() for k, v in plain.run(q1[:R // 2].contiguous(), v1[:R // 2].contiguous(), H_sim).items() if v is not None}
+    assert out["status"].all(), out["failed_at"]
+    assert np.array_equal(out["q"][:, :R // 2], ref["q"])
+    qn, qp = out["q"][:, 0], out["q"][:, R // 2]
+    assert np.abs(qn - qp).max() > 1e-3                                  # the payload changes the motion …
+    assert np.abs(qp[-1, 1] - qn[-1, 1]) < 0.05                          # … but the robot keeps walking at height
+    gn, gp = out["gamma"][:, 0].sum(), out["gamma"][:, R // 2].sum()
+    assert gp > 1.1 * gn                                                 # 3 kg on 14.5 kg: ≈ 20 % more normal impulse
+
+
 def test_grouped_rollouts_are_bit_identical(cuda_device):
     """`GroupedRollouts` (independent parts on their own streams / host threads) changes scheduling only."""
     import torch
