@@ -43,6 +43,43 @@ IP_KW = dict(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, diff_sol=True)  # monte_c
 METRIC = "contact_subproblems_per_sec"
 UNIT = "subproblems/s"
 
+# BASELINE.json `configs` 2-5 as IP-sweep workloads (config 1 is the CPU-only hopper call, tests/test_oracle.py).
+# rollouts × H_mpc subproblems per step and GPU; `alt`: non-zero altitude offsets on the impact rows (config 3:
+# examples/flamingo/piecewise.jl runs the flat-linearized policy with measured altitudes).
+CONFIGS = {
+    2: dict(robot="quadruped", mode="configuration", H=10, rollouts=4096, alt=False,
+            ip=dict(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, diff_sol=True),
+            name="quadruped flat gait2, H_mpc=10, 4096 Monte-Carlo rollouts (examples/quadruped/monte_carlo.jl:27-58)"),
+    3: dict(robot="flamingo", mode="configurationforce", H=15, rollouts=1093, alt=True,
+            ip=dict(r_tol=1e-8, kappa_tol=1e-4, max_iter=100, diff_sol=True, undercut=5.0, gamma_reg=0.1),
+            name="flamingo gait_forward_36_4, H_mpc=15, :configurationforce, 16 395-problem IP batch with non-zero altitude "
+                 "offsets (examples/flamingo/piecewise.jl:24-48; ip_opts defaults of ci_mpc_policy, policy.jl:54-61)"),
+    4: dict(robot="quadruped", mode="configuration", H=10, rollouts=65536, alt=False,
+            ip=dict(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, diff_sol=True),
+            name="quadruped flat gait2, H_mpc=10, 65536 Monte-Carlo rollouts per GPU"),
+    5: dict(robot="centroidal_quadruped", mode="configuration", H=20, rollouts=13108, alt=False,
+            ip=dict(r_tol=1e-4, kappa_tol=2e-4, max_iter=100, diff_sol=True, undercut=5.0),
+            name="centroidal_quadruped inplace_trot_v4, H_mpc=20, 13 108 rollouts = 262 160 subproblems ('256k batch') per GPU "
+                 "(examples/centroidal_quadruped/flat_trot.jl:31-62); the payload only changes the simulated plant, "
+                 "not this kernel (cimpc_create_named)"),
+}
+
+
+def executed_flops(nq, nu, nw, nc, nb, mode, mean_iters, evals_per_iter=1.0):
+    """Flops THIS implementation executes per subproblem (csrc/ip_kernel.cuh; FMA = 2 flops, useful lanes only): per
+    iteration the assembly of the reduced (nc+nb)² block, its in-place Gauss-Jordan inversion (ψ passenger rows
+    included), CAi·r and Ai·r, two inverse applications with the ψ recovery, Δx, and `evals_per_iter` candidate
+    residuals; once per subproblem the θ prologue, the first residual, and the sensitivities (a second inversion,
+    P1 = AiB S⁻¹, and the products with the 2nq+nu consumed columns of W)."""
+    nx, ny, nr, npsi = nq, 2 * nc + nb, nc + nb, nc
+    nth, ncol, nfr = 2 * nq + nu + nw + 2, 2 * nq + nu, 1 + nb // nc
+    nyd = nr if mode == "configurationforce" else 0
+    res = 2 * (nx + ny) ** 2
+    per_it = 3 * nr ** 2 + 2 * nr ** 3 + 2 * nr ** 2 * npsi + 4 * nx * ny + 2 * (2 * nr ** 2 + 2 * nfr * npsi) + 2 * nx * nr \
+        + evals_per_iter * res
+    once = 2 * nth * (nx + ny) + res + 9 * nr ** 2 + 2 * nr ** 3 + 2 * nx * nr ** 2 + 2 * ncol * nr * (nx + nyd)
+    return mean_iters * per_it + once
+
 
 def algorithmic_bytes(nq, nu, nw, nc, nb, mode):
     """SURVEY.md §8d / BASELINE.md §3: read θ, q2 guess, alt; write d, δq0, δq1, δu1, status, iters."""
@@ -59,19 +96,97 @@ def algorithmic_flops(nq, nu, nc, nb, mean_iters):
     return mean_iters * f_it + f_d
 
 
-def build_workload(rank: int, rollouts: int):
+def build_workload(rank: int, rollouts: int, cfg=None):
     """Stage-major batch: subproblem (stage i, rollout r) uses knot i (all rollouts share the window,
-    policy.jl:100-107, 131) with rollout-specific perturbed θ and cold-start q2."""
+    policy.jl:100-107, 131) with rollout-specific perturbed θ and cold-start q2.
+    Returns lin, knot, θ, q2, alt (None unless the config asks for altitude offsets)."""
     from common import SIZES, load_gait, load_lin, make_batch
-    lin, gait = load_lin(ROBOT), load_gait(ROBOT)
-    n = rollouts * H_MPC
-    knot, theta, q2 = make_batch(ROBOT, lin, gait, n, seed=100 + rank)
-    # make_batch cycles knots 0..H_ref-1; restrict to the MPC window 0..H_MPC-1, stage-major
-    nq = SIZES[ROBOT][0]
+    cfg = cfg or CONFIGS[4]
+    robot, H = cfg["robot"], cfg["H"]
+    lin, gait = load_lin(robot), load_gait(robot)
+    n = rollouts * H
+    knot, theta, q2 = make_batch(robot, lin, gait, n, seed=100 + rank)
+    # make_batch cycles knots 0..H_ref-1; restrict to the MPC window 0..H-1, stage-major
+    nq, nc = SIZES[robot][0], SIZES[robot][3]
     stage = (np.arange(n) // rollouts).astype(np.int32)
     theta = theta - lin["th0"][knot] + lin["th0"][stage]
     q2 = q2 - lin["z0"][knot, :nq] + lin["z0"][stage, :nq]
-    return lin, stage, np.ascontiguousarray(theta), np.ascontiguousarray(q2)
+    alt = None
+    if cfg.get("alt"):  # piecewise terrain: steps of up to 2 cm under the feet, one altitude vector per rollout
+        rng = np.random.Generator(np.random.Philox(7000 + rank))
+        alt = np.ascontiguousarray(np.tile(0.02 * rng.random((rollouts, nc)), (H, 1)))
+    return lin, stage, np.ascontiguousarray(theta), np.ascontiguousarray(q2), alt
+
+
+def ip_sweep_leg(cb, torch, dev, cfg, rank, steps, warmup, rollouts=None):
+    """Device-resident throughput of one `implicit_dynamics!` sweep of a BASELINE config: value, ms, both rooflines."""
+    from common import SIZES
+    robot, mode = cfg["robot"], cfg["mode"]
+    nq, nu, nw, nc, nb = SIZES[robot]
+    lin, knot, theta, q2, alt = build_workload(rank, rollouts or cfg["rollouts"], cfg)
+    n = knot.shape[0]
+    im = cb.ImplicitTrajectory(nq, nu, nw, nc, nb, lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"], mode=mode,
+                               opts=cb.InteriorPointOptions(**cfg["ip"]), device=dev.index or 0)
+    kd, td, qd = torch.from_numpy(knot).to(dev), torch.from_numpy(theta).to(dev), torch.from_numpy(q2).to(dev)
+    ad = torch.from_numpy(alt).to(dev) if alt is not None else None
+    outb = im.solve_device(kd, td, qd, alt=ad)
+    for _ in range(warmup):
+        im.solve_device(kd, td, qd, alt=ad, out=outb)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        im.solve_device(kd, td, qd, alt=ad, out=outb)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    mean_it = float(outb[3].double().mean().item())
+    peaks, peak_kind = measured_peaks()
+    f_peak, f_kind = fp64_peak()
+    B = algorithmic_bytes(nq, nu, nw, nc, nb, mode)
+    fl_ref = algorithmic_flops(nq, nu, nc, nb, mean_it)
+    fl_exe = executed_flops(nq, nu, nw, nc, nb, mode, mean_it)
+    gbs = n * B / (ms * 1e-3) / 1e9
+    res = {"workload": cfg["name"], "robot": robot, "mode": mode, "H_mpc": cfg["H"], "subproblems_per_step": int(n),
+           "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "mean_ip_iterations": mean_it,
+           "converged_frac": float(outb[2].double().mean().item()), "lanes_per_subproblem": im.group,
+           "l2": "inputs + outputs per step exceed the 126 MB L2" if n * B > 126e6 else
+                 f"inputs + outputs per step = {n * B / 1e6:.0f} MB < 126 MB L2: resident after warm-up (a {cfg['rollouts']}-rollout "
+                 "batch is this small by definition of the config)",
+           "roofline": {"bound": "hbm", "kernel": "ip_solve_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_subproblem": B, "traffic": None},
+           "fp64": {"peak": f_peak, "unit": "TFLOP/s",
+                    "executed": {"achieved": n * fl_exe / (ms * 1e-3) / 1e12, "frac": n * fl_exe / (ms * 1e-3) / 1e12 / f_peak,
+                                 "flops_per_subproblem": fl_exe},
+                    "reference_count": {"achieved": n * fl_ref / (ms * 1e-3) / 1e12,
+                                        "frac": n * fl_ref / (ms * 1e-3) / 1e12 / f_peak, "flops_per_subproblem": fl_ref}}}
+    im.close()
+    return res
+
+
+def pin_to_gpu_numa(local: int):
+    """Bind this rank's host threads (and therefore its first-touch pinned allocations) to the NUMA node of its GPU
+    (/sys/bus/pci/devices/<bus id>/local_cpulist); best effort, reported in the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev_id = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0"
+        with open(os.path.join(path, "local_cpulist")) as f:
+            txt = f.read().strip()
+        with open(os.path.join(path, "numa_node")) as f:
+            node = int(f.read().strip())
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "error": type(e).__name__}
 
 
 class ClockSampler:
@@ -191,37 +306,51 @@ def fp64_peak():
     return 37.2, "nominal 148 SM x 64 DFMA/clk x 1.965 GHz"
 
 
-def cpu_baseline_run(lin, knot, theta, q2, sample: int, threads: int = 0):
+def cpu_baseline_run(lin, knot, theta, q2, sample: int, threads: int = 0, cfg=None, alt=None):
     from common import SIZES
     from oracle.c_oracle import COracle
     from oracle.ip import IPOptions
-    co = COracle(*SIZES[ROBOT], lin, mode=MODE, solver="mgs")
-    o = IPOptions(**IP_KW)
-    co.solve(knot[:2048], theta[:2048], q2[:2048], o, threads=threads)  # warm-up (page-in, thread pool)
+    cfg = cfg or CONFIGS[4]
+    co = COracle(*SIZES[cfg["robot"]], lin, mode=cfg["mode"], solver="mgs")
+    o = IPOptions(**cfg["ip"])
+    a = (lambda k: None) if alt is None else (lambda k: alt[:k])
+    co.solve(knot[:2048], theta[:2048], q2[:2048], o, threads=threads, alt=a(2048))  # warm-up (page-in, thread pool)
     t0 = time.perf_counter()
-    z, dz, st, it = co.solve(knot[:sample], theta[:sample], q2[:sample], o, threads=threads)
+    z, dz, st, it = co.solve(knot[:sample], theta[:sample], q2[:sample], o, threads=threads, alt=a(sample))
     dt = time.perf_counter() - t0
     return sample / dt, co.max_threads if threads <= 0 else threads, dt, float(it.mean()), float(st.mean())
 
 
+def config_block(cfg, world, rollouts, n):
+    """The `config` object of the JSON line — identical in both arms (`--impl ours` / `--impl reference`)."""
+    return {"workload": cfg["name"], "config_id": cfg["id"], "robot": cfg["robot"], "mode": cfg["mode"], "H_mpc": cfg["H"],
+            "rollouts_per_gpu": int(rollouts), "subproblems_per_step_per_gpu": int(n), **cfg["ip"],
+            "l2": "inputs+outputs per step exceed the 126 MB L2" if n * 3000 > 126e6 else "batch smaller than L2 (config size)",
+            "parallelism": f"rollout-sharded x{world}, no data-path collective"}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's algorithm (C restatement: explicit Dx⁻¹, MGS-QR per
-    iteration, all nθ sensitivity columns) on the host cores; rank 0 only."""
+    iteration, all nθ sensitivity columns) on the host cores; rank 0 only.  Each step is a bounded sample (1/8 of the
+    per-GPU batch, at most 81 920 subproblems) of the SAME workload as the `ours` arm; the metric is a rate."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    lin, knot, theta, q2 = build_workload(0, ROLLOUTS_PER_GPU // 8)
-    n = knot.shape[0]  # 81 920 subproblems per step (1/8 of the per-GPU batch)
+    cfg = dict(CONFIGS[args.config], id=args.config)
+    rollouts = args.rollouts or cfg["rollouts"]
+    sample_rollouts = max(1, min(rollouts // 8, 8192)) if rollouts >= 64 else rollouts
+    lin, knot, theta, q2, alt = build_workload(0, sample_rollouts, cfg)
+    n = knot.shape[0]
     from common import SIZES
     from oracle.c_oracle import COracle
     from oracle.ip import IPOptions
-    co = COracle(*SIZES[ROBOT], lin, mode=MODE, solver="mgs")
-    o = IPOptions(**IP_KW)
+    co = COracle(*SIZES[cfg["robot"]], lin, mode=cfg["mode"], solver="mgs")
+    o = IPOptions(**cfg["ip"])
     for _ in range(max(args.warmup, 1)):
-        co.solve(knot, theta, q2, o)
+        co.solve(knot, theta, q2, o, alt=alt)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        z, dz, st, it = co.solve(knot, theta, q2, o)
+        z, dz, st, it = co.solve(knot, theta, q2, o, alt=alt)
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     cores = co.max_threads
@@ -229,11 +358,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"quadruped flat gait2 H_mpc=10 linearized IP sweep, bounded sample of "
-                               f"{n} subproblems/step of the 655360-subproblem batch", "mode": MODE, **IP_KW},
+        "config": config_block(cfg, args.gpus, rollouts, rollouts * cfg["H"]),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} subproblems x {args.steps} steps; C restatement of the Julia CPU path "
-                                   f"(oracle/c/ip_oracle.c, OpenMP over problems)"},
+                         "sample": f"{n} subproblems ({sample_rollouts} rollouts of the batch) x {args.steps} steps; C restatement "
+                                   f"of the Julia CPU path (oracle/c/ip_oracle.c, OpenMP over problems)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mean_ip_iterations": float(it.mean()), "converged_frac": float(st.mean()),
     }
@@ -246,7 +374,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rollouts", type=int, default=ROLLOUTS_PER_GPU, help="rollouts per GPU (default 65536)")
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS), help="BASELINE.json config (default 4)")
+    ap.add_argument("--rollouts", type=int, default=None, help="rollouts per GPU (default: the config's)")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the extra.configs legs (configs 2, 3, 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mpc", action="store_true", help="skip the batched newton_solve! (MPC steps/s) leg")
     ap.add_argument("--mpc-rollouts", type=int, default=16384)
@@ -271,8 +401,13 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    numa = pin_to_gpu_numa(local)
+    cfg = dict(CONFIGS[args.config], id=args.config)
+    if args.rollouts is None:
+        args.rollouts = cfg["rollouts"]
+    ROBOT, MODE, H_MPC, IP_KW = cfg["robot"], cfg["mode"], cfg["H"], cfg["ip"]
     nq, nu, nw, nc, nb = SIZES[ROBOT]
-    lin, knot, theta, q2 = build_workload(rank, args.rollouts)
+    lin, knot, theta, q2, alt = build_workload(rank, args.rollouts, cfg)
     n = knot.shape[0]
     opts = cb.InteriorPointOptions(**IP_KW)
     im = cb.ImplicitTrajectory(nq, nu, nw, nc, nb, lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
@@ -282,9 +417,10 @@ def main():
     kd = torch.from_numpy(knot).to(dev)
     td = torch.from_numpy(theta).to(dev)
     qd = torch.from_numpy(q2).to(dev)
-    outb = im.solve_device(kd, td, qd)
+    ad = torch.from_numpy(alt).to(dev) if alt is not None else None
+    outb = im.solve_device(kd, td, qd, alt=ad)
     for _ in range(args.warmup):
-        im.solve_device(kd, td, qd, out=outb)
+        im.solve_device(kd, td, qd, alt=ad, out=outb)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -298,7 +434,7 @@ def main():
     t_wall0 = time.time()
     ev[0].record()
     for s in range(args.steps):
-        im.solve_device(kd, td, qd, out=outb)
+        im.solve_device(kd, td, qd, alt=ad, out=outb)
         ev[s + 1].record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
@@ -333,28 +469,38 @@ def main():
     h2d = knot_h.numel() * 4 + theta_h.numel() * 8 + q2_h.numel() * 8
     d2h = z_h.numel() * 8 + dz_h.numel() * 8 + st_h.numel() + it_h.numel() * 4
 
-    def e2e_once():
-        im.solve_host_into(knot_h.numpy(), theta_h.numpy(), q2_h.numpy(), None, z_h.numpy(), dz_h.numpy(),
-                           st_h.numpy(), it_h.numpy())
+    alt_h = torch.from_numpy(alt).pin_memory() if alt is not None else None
+    if alt_h is not None:
+        h2d += alt_h.numel() * 8
 
-    e2e_once()
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_once()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    def e2e_once(mask=None):
+        im.solve_host_into(knot_h.numpy(), theta_h.numpy(), q2_h.numpy(), alt_h.numpy() if alt_h is not None else None,
+                           z_h.numpy(), dz_h.numpy(), st_h.numpy(), it_h.numpy(), out_mask=mask)
+
+    def timed_e2e(mask=None):
+        e2e_once(mask)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_once(mask)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    e2e_s = timed_e2e()
     e2e_ok = bool(np.array_equal(z_h.numpy(), outb[0].cpu().numpy()))
+    # the same call returning only what a caller of implicit_dynamics! that does not run Newton needs: d and the status
+    mask_d = im.OUT_ZHEAD | im.OUT_STATUS
+    e2e_d_s = timed_e2e(mask_d)
+    d2h_d = n * im.nd * 8 + st_h.numel() + it_h.numel() * 4
 
     # ---- MPC-step leg: batched newton_solve! (cold start, one MPC step of every rollout) --------------
     mpc = None
-    if not args.no_mpc:
+    if not args.no_mpc and ROBOT == "quadruped":
         from common import load_gait
         gait = load_gait(ROBOT)
         Rm = min(args.rollouts, args.mpc_rollouts)
@@ -381,7 +527,28 @@ def main():
         if dist:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         inf = infom.double().mean(0).cpu().numpy()
-        mpc = {"value": Rm * world * m_steps / (float(tm.item()) * 1e-3), "unit": "MPC steps/s",
+        # end to end at the path's own boundary: host q0, q1 in, host u out (cimpc_newton_solve_batch_host)
+        q0h, q1h = q0m.cpu().pin_memory(), q1m.cpu().pin_memory()
+        uh = torch.empty((Rm, nu), dtype=torch.float64).pin_memory()
+        ih = torch.empty((Rm, 4), dtype=torch.int32).pin_memory()
+
+        def mpc_host_once():
+            newton.solve_host(win, gait["q"][:H_MPC + 2], gait["u"][:H_MPC], gait["mu"], gait["h"], q0h.numpy(), q1h.numpy(),
+                              u_out=uh.numpy(), info_out=ih.numpy())
+        mpc_host_once()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(m_steps):
+            mpc_host_once()
+        th = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        mpc_e2e = {"value": Rm * world * m_steps / float(th.item()), "unit": "MPC steps/s",
+                   "h2d_bytes_per_step": int(2 * Rm * nq * 8), "d2h_bytes_per_step": int(Rm * nu * 8 + Rm * 16),
+                   "matches_device_leg": bool(np.array_equal(uh.numpy(), um.cpu().numpy())),
+                   "api": "cimpc_newton_solve_batch_host (pinned host q0, q1 in; host u, info out; one graph launch)"}
+        mpc = {"value": Rm * world * m_steps / (float(tm.item()) * 1e-3), "unit": "MPC steps/s", "e2e": mpc_e2e,
                "rollouts_per_gpu": Rm, "steps": m_steps, "ms_per_mpc_step_batch": float(tm.item()) / m_steps,
                "mean_newton_iterations": float(inf[0]), "mean_implicit_dynamics_sweeps": float(inf[1]),
                "converged_frac": float(inf[2]), "sweeps_per_call": newton.last_sweeps,
@@ -395,7 +562,7 @@ def main():
 
     # ---- closed-loop leg: the Monte-Carlo workload itself (policy + simulator on the device) ----------
     closed = None
-    if not args.no_mpc and not args.no_closed_loop:
+    if not args.no_mpc and not args.no_closed_loop and ROBOT == "quadruped":
         Rc = min(args.rollouts, args.mpc_rollouts)
         N_sample = 5
         # the rollouts run as `--closed-loop-groups` independent parts (own stream + host thread each): one part's
@@ -440,6 +607,13 @@ def main():
                             "(Philox seed 100), policy every 5 simulator steps, nonlinear simulator step on the device; "
                             "trajectories recorded every 5th step and gathered to rank 0"}
 
+    # ---- the other BASELINE configs, so that the driver's record holds them (rank 0, one GPU each) ----------------
+    extra = None
+    if args.config == 4 and not args.no_extra_configs and rank == 0:
+        extra = [dict(ip_sweep_leg(cb, torch, dev, dict(CONFIGS[c], id=c), 0, max(args.steps, 5), args.warmup), config_id=c)
+                 for c in (2, 3, 5)]
+    if dist:
+        dist.barrier()
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -451,45 +625,58 @@ def main():
     B = algorithmic_bytes(nq, nu, nw, nc, nb, MODE)
     achieved = n * B / (kernel_ms * 1e-3) / 1e9
     fl = algorithmic_flops(nq, nu, nc, nb, mean_it)
+    fl_exe = executed_flops(nq, nu, nw, nc, nb, MODE, mean_it)
     f_peak, f_kind = fp64_peak()
     f_ach = n * fl / (kernel_ms * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "ip_kernel_traffic.json")
-    if os.path.exists(tp):
+    f_exe = n * fl_exe / (kernel_ms * 1e-3) / 1e12
+    # DRAM traffic of the kernel cannot be read without a profiler; the number below comes from the committed
+    # `ncu --set full` capture of this round's kernel (per-subproblem streaming traffic × n), and says so.
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r02_ip_kernel_traffic.json")
+    if os.path.exists(tp) and ROBOT == "quadruped":
         with open(tp) as f:
-            # measured on an 81 920-subproblem launch; DRAM traffic is per-subproblem streaming, so scale to n
-            traffic = json.load(f).get("dram_bytes_per_subproblem") * n
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_subproblem") * n
+        traffic_src = f"profiles/r02_ip_kernel_traffic.json ({tj.get('source', 'ncu --set full')}), scaled to this launch; not measured in this run"
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"quadruped flat gait2, H_mpc={H_MPC}, {args.rollouts} Monte-Carlo rollouts per GPU = "
-                               f"{n} cold-started linearized IP subproblems per step per GPU (one implicit_dynamics! sweep)",
-                   "mode": MODE, **IP_KW, "l2": "inputs+outputs per step (2.2 GB) exceed the 126 MB L2",
-                   "parallelism": f"rollout-sharded x{world}, no data-path collective"},
+        "config": config_block(cfg, world, args.rollouts, n),
         "mean_ip_iterations": mean_it, "max_ip_iterations": max_it, "converged_frac": conv_frac,
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": n * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "matches_device_leg": e2e_ok,
-                "api": "cimpc_ip_solve_batch_host (pinned host buffers, chunk-pipelined H2D / kernel / D2H)"},
+                "api": "cimpc_ip_solve_batch_host (pinned host buffers, chunk-pipelined H2D / kernel / D2H; z, δz, status, "
+                       "iters all returned)", "host_numa": numa,
+                "d_and_status_only": {"value": n * world * e2e_steps / e2e_d_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                                      "d2h_bytes_per_step": int(d2h_d),
+                                      "api": "cimpc_ip_solve_batch_host_ex, mask CIMPC_OUT_ZHEAD | CIMPC_OUT_STATUS (δz stays "
+                                             "on the device: only newton_solve! consumes it)"}},
         "roofline": {"bound": "hbm", "kernel": "ip_solve_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                     "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})", "algorithmic_bytes_per_subproblem": B,
                      "kernel_ms": kernel_ms,
                      "note": "fp64-issue bound path: HBM fraction is structurally small (SURVEY.md §8d); see fp64"},
-        "fp64": {"achieved": f_ach, "peak": f_peak, "unit": "TFLOP/s", "frac": f_ach / f_peak,
-                 "flops_per_subproblem": fl, "peak_source": f_kind,
-                 "note": "flops counted as the REFERENCE algorithm would spend them (BASELINE.md §3)"},
+        "fp64": {"peak": f_peak, "unit": "TFLOP/s", "peak_source": f_kind,
+                 "executed": {"achieved": f_exe, "frac": f_exe / f_peak, "flops_per_subproblem": fl_exe,
+                              "note": "flops this kernel executes (reduced 12x12 Gauss-Jordan inverse, 11 consumed sensitivity "
+                                      "solves as products)"},
+                 "reference_count": {"achieved": f_ach, "frac": f_ach / f_peak, "flops_per_subproblem": fl,
+                                     "note": "flops the REFERENCE algorithm would spend (MGS-QR 16x16, all 34 sensitivity "
+                                             "columns; BASELINE.md §3)"}},
     }
+    if extra is not None:
+        out["extra"] = {"configs": extra}
     if mpc is not None:
         out["mpc_steps"] = mpc
     if closed is not None:
         out["closed_loop"] = closed
     if not args.no_cpu_baseline and world == 1:
         sample = min(n, 262144)
-        v, cores, dt, mit, conv = cpu_baseline_run(lin, knot, theta, q2, sample)
+        v, cores, dt, mit, conv = cpu_baseline_run(lin, knot, theta, q2, sample, cfg=cfg, alt=alt)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": f"first {sample} subproblems of the same batch, {dt:.1f} s wall; C restatement "
                                          f"of the Julia CPU path (explicit Dx^-1, MGS-QR per iteration, all n_theta "

@@ -21,7 +21,7 @@ SYMBOLS = [
     "cimpc_newton_opts_default", "cimpc_newton_create", "cimpc_newton_solve_batch", "cimpc_newton_last_sweeps",
     "cimpc_sim_step_batch", "cimpc_linearize", "cimpc_get_linearization",
     "cimpc_newton_create_ex", "cimpc_newton_solve_batch_ex", "cimpc_newton_solve_batch_ex2",
-    "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex", "cimpc_newton_create_dense", "cimpc_create_named",
+    "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex", "cimpc_newton_create_dense", "cimpc_create_named", "cimpc_ip_solve_batch_host_ex",
 ]
 
 
@@ -88,6 +88,8 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_ip_solve_batch.restype = C.c_int
     lib.cimpc_ip_solve_batch_host.argtypes = [vp, i64, dp, dp, dp, dp, C.POINTER(IPOpts), dp, dp, dp, dp]
     lib.cimpc_ip_solve_batch_host.restype = C.c_int
+    lib.cimpc_ip_solve_batch_host_ex.argtypes = [vp, i64, dp, dp, dp, dp, C.POINTER(IPOpts), dp, dp, dp, dp, C.c_uint32]
+    lib.cimpc_ip_solve_batch_host_ex.restype = C.c_int
     lib.cimpc_launch_count.argtypes = [vp]
     lib.cimpc_launch_count.restype = C.c_int64
     lib.cimpc_newton_opts_default.argtypes = [C.POINTER(NewtonOpts)]

@@ -725,7 +725,19 @@ static bool is_pinned(const void* p) {
 int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, const double* theta,
                               const double* q2_init, const double* alt, const cimpc_ip_opts* opts,
                               double* z_out, double* dz_out, uint8_t* status, int32_t* iters) {
-  int rc = check_solve_args(ctx, n, knot, theta, q2_init, opts, z_out, dz_out, status, iters);
+  return cimpc_ip_solve_batch_host_ex(ctx, n, knot, theta, q2_init, alt, opts, z_out, dz_out, status, iters,
+                                      CIMPC_OUT_Z | CIMPC_OUT_DZ | CIMPC_OUT_STATUS);
+}
+
+int cimpc_ip_solve_batch_host_ex(cimpc_ctx* ctx, int64_t n, const int32_t* knot, const double* theta,
+                                 const double* q2_init, const double* alt, const cimpc_ip_opts* opts,
+                                 double* z_out, double* dz_out, uint8_t* status, int32_t* iters, uint32_t out_mask) {
+  const bool want_zfull = (out_mask & CIMPC_OUT_Z) != 0, want_zhead = !want_zfull && (out_mask & CIMPC_OUT_ZHEAD) != 0;
+  const bool want_dz = (out_mask & CIMPC_OUT_DZ) != 0, want_st = (out_mask & CIMPC_OUT_STATUS) != 0;
+  // buffers that are not copied back need not be provided
+  int rc = check_solve_args(ctx, n, knot, theta, q2_init, opts, (want_zfull || want_zhead) ? (void*)z_out : (void*)ctx,
+                            (want_dz || !opts || !opts->diff_sol) ? (void*)dz_out : (void*)ctx,
+                            want_st ? (void*)status : (void*)ctx, want_st ? (void*)iters : (void*)ctx);
   if (rc != CIMPC_OK) return rc;
   if (n == 0) return CIMPC_OK;
   for (int64_t i = 0; i < n; ++i)
@@ -734,6 +746,7 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
   const LinLayout& l = ctx->entry->lay;
   const int nc = ctx->entry->desc.nc;
   const bool diff = opts->diff_sol != 0;
+  const bool copy_dz = diff && want_dz;
   constexpr int NS = cimpc_ctx::NS;
   const int64_t C = n < cimpc_ctx::CHUNK ? n : cimpc_ctx::CHUNK;  // subproblems per chunk
   // per-slot layout (bytes)
@@ -745,7 +758,8 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
   const size_t o_z = o_alt + b_alt, o_dz = o_z + b_z, o_st = o_dz + b_dz, o_it = o_st + b_st;
   const size_t slot = o_it + b_it;
   const bool pin_in = is_pinned(knot) && is_pinned(theta) && is_pinned(q2_init) && is_pinned(alt);
-  const bool pin_out = is_pinned(z_out) && (!diff || is_pinned(dz_out)) && is_pinned(status) && is_pinned(iters);
+  const bool pin_out = (!(want_zfull || want_zhead) || is_pinned(z_out)) && (!copy_dz || is_pinned(dz_out)) &&
+                       (!want_st || (is_pinned(status) && is_pinned(iters)));
   if (ctx->dev_bytes < slot * NS) {
     if (ctx->dev) cudaFree(ctx->dev);
     ctx->dev = nullptr; ctx->dev_bytes = 0;
@@ -762,10 +776,14 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
   auto drain = [&](int64_t c) {  // copy staged outputs of chunk c to the caller (pageable outputs only)
     const int64_t lo = c * C, m = (n - lo < C) ? (n - lo) : C;
     const char* hp = (const char*)ctx->pin + (size_t)(c % NS) * slot;
-    std::memcpy(z_out + lo * l.nz, hp + o_z, m * l.nz * 8);
-    if (diff) std::memcpy(dz_out + lo * (size_t)l.nd * l.ncol, hp + o_dz, m * (size_t)l.nd * l.ncol * 8);
-    std::memcpy(status + lo, hp + o_st, m);
-    std::memcpy(iters + lo, hp + o_it, m * 4);
+    if (want_zfull) std::memcpy(z_out + lo * l.nz, hp + o_z, m * l.nz * 8);
+    if (want_zhead)
+      for (int64_t i = 0; i < m; ++i) std::memcpy(z_out + (lo + i) * l.nz, hp + o_z + i * l.nz * 8, l.nd * 8);
+    if (copy_dz) std::memcpy(dz_out + lo * (size_t)l.nd * l.ncol, hp + o_dz, m * (size_t)l.nd * l.ncol * 8);
+    if (want_st) {
+      std::memcpy(status + lo, hp + o_st, m);
+      std::memcpy(iters + lo, hp + o_it, m * 4);
+    }
   };
   for (int64_t c = 0; c < nchunks; ++c) {
     const int sl = (int)(c % NS);
@@ -798,10 +816,14 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
     void* t_dz = !diff ? nullptr : (pin_out ? (void*)(dz_out + lo * (size_t)l.nd * l.ncol) : (void*)(hp + o_dz));
     void* t_st = pin_out ? (void*)(status + lo) : (void*)(hp + o_st);
     void* t_it = pin_out ? (void*)(iters + lo) : (void*)(hp + o_it);
-    CK(cudaMemcpyAsync(t_z, dp + o_z, m * l.nz * 8, cudaMemcpyDeviceToHost, s));
-    if (diff) CK(cudaMemcpyAsync(t_dz, dp + o_dz, m * (size_t)l.nd * l.ncol * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(t_st, dp + o_st, m, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(t_it, dp + o_it, m * 4, cudaMemcpyDeviceToHost, s));
+    if (want_zfull) CK(cudaMemcpyAsync(t_z, dp + o_z, m * l.nz * 8, cudaMemcpyDeviceToHost, s));
+    if (want_zhead)  // only z*[1:nd] of every subproblem (what `d` needs), same nz stride on both sides
+      CK(cudaMemcpy2DAsync(t_z, l.nz * 8, dp + o_z, l.nz * 8, l.nd * 8, m, cudaMemcpyDeviceToHost, s));
+    if (copy_dz) CK(cudaMemcpyAsync(t_dz, dp + o_dz, m * (size_t)l.nd * l.ncol * 8, cudaMemcpyDeviceToHost, s));
+    if (want_st) {
+      CK(cudaMemcpyAsync(t_st, dp + o_st, m, cudaMemcpyDeviceToHost, s));
+      CK(cudaMemcpyAsync(t_it, dp + o_it, m * 4, cudaMemcpyDeviceToHost, s));
+    }
   }
   for (int64_t c = (nchunks > NS ? nchunks - NS : 0); c < nchunks; ++c) {
     CK(cudaStreamSynchronize(ctx->streams[c % NS]));

@@ -163,23 +163,27 @@ class ImplicitTrajectory:
             dz = np.transpose(dz, (0, 2, 1))  # column-major nd×ncol per problem → [n, row, col]
         return z, dz, status.astype(bool), iters
 
+    OUT_Z, OUT_DZ, OUT_STATUS, OUT_ZHEAD = 1, 2, 4, 8
+
     def solve_host_into(self, knot, theta, q2_init, alt, z, dz, status, iters,
-                        opts: InteriorPointOptions | None = None):
+                        opts: InteriorPointOptions | None = None, out_mask: int | None = None):
         """Same call writing into caller-owned numpy arrays (e.g. views of pinned torch tensors):
-        z (n, nz), dz (n, ncol, nd) [the C ABI's per-problem column-major nd×ncol], status uint8, iters int32."""
+        z (n, nz), dz (n, ncol, nd) [the C ABI's per-problem column-major nd×ncol], status uint8, iters int32.
+        out_mask: which results are copied back (`cimpc_ip_solve_batch_host_ex`); None = everything."""
         o = (opts or self.opts)
         n = knot.shape[0]
         for a in (knot, theta, q2_init, z, status, iters):
             assert a.flags["C_CONTIGUOUS"]
         assert knot.dtype == np.int32 and status.dtype == np.uint8 and iters.dtype == np.int32
         assert theta.shape == (n, self.ntheta) and q2_init.shape == (n, self.nq) and z.shape == (n, self.nz)
-        if o.diff_sol:
+        mask = (self.OUT_Z | self.OUT_DZ | self.OUT_STATUS) if out_mask is None else int(out_mask)
+        if o.diff_sol and (mask & self.OUT_DZ):
             assert dz is not None and dz.shape == (n, self.ncol, self.nd) and dz.flags["C_CONTIGUOUS"]
         co = o.to_c()
-        capi.check(self._ctx, self.lib.cimpc_ip_solve_batch_host(
+        capi.check(self._ctx, self.lib.cimpc_ip_solve_batch_host_ex(
             self._ctx, n, knot.ctypes.data, theta.ctypes.data, q2_init.ctypes.data,
             alt.ctypes.data if alt is not None else None, C.byref(co), z.ctypes.data,
-            dz.ctypes.data if (dz is not None and o.diff_sol) else None, status.ctypes.data, iters.ctypes.data))
+            dz.ctypes.data if (dz is not None and o.diff_sol) else None, status.ctypes.data, iters.ctypes.data, mask))
 
     # -- batched solve, DEVICE buffers (torch CUDA tensors; torch is plumbing only) --
     def solve_device(self, knot, theta, q2_init, alt=None, out=None, opts: InteriorPointOptions | None = None,

@@ -177,6 +177,21 @@ int cimpc_ip_solve_batch_host(cimpc_ctx* ctx, int64_t n, const int32_t* knot, co
                               double* z_out, double* dz_out, uint8_t* status, int32_t* iters);
 
 
+/*
+ * Same call with an OUTPUT MASK: only the selected results travel back over the bus (buffers of unselected outputs may be
+ * NULL).  δz is 89 % of the output bytes and only `newton_solve!` consumes it — a caller that wants the dynamics
+ * violation `d = z*[1:nd] − [q2; γ; b]` (implicit_dynamics.jl:180-190) and the status passes
+ * CIMPC_OUT_ZHEAD | CIMPC_OUT_STATUS: z_out keeps its nz stride, only the first nd entries of every column are written.
+ */
+#define CIMPC_OUT_Z 1u      /* z*  (nz per subproblem)                  */
+#define CIMPC_OUT_DZ 2u     /* δz  (nd × ncol per subproblem)            */
+#define CIMPC_OUT_STATUS 4u /* status and iteration count                */
+#define CIMPC_OUT_ZHEAD 8u  /* z*[1:nd] only (ignored with CIMPC_OUT_Z)  */
+int cimpc_ip_solve_batch_host_ex(cimpc_ctx* ctx, int64_t n, const int32_t* knot, const double* theta,
+                                 const double* q2_init, const double* alt, const cimpc_ip_opts* opts,
+                                 double* z_out, double* dz_out, uint8_t* status, int32_t* iters, uint32_t out_mask);
+
+
 /* ------------------------------------------------------------------------------------------------
  * Batched `newton_solve!` (src/controller/newton.jl:169-288) for n_rollouts Monte-Carlo rollouts that
  * track the same reference window (policy.jl:100-107, 131): one call = one MPC step of every rollout.
