@@ -594,15 +594,18 @@ def main():
             dist.all_reduce(tc, op=dist.ReduceOp.MAX)
             dist.all_reduce(okc, op=dist.ReduceOp.SUM)
             okc /= world
-            # final gather of the (down-sampled: every N_sample-th step) configurations to rank 0 over NCCL
-            qg = cb.gather_rollout_results(res_c["q"].permute(1, 0, 2).contiguous(), Rc * world)
+            # final gather of the (down-sampled: every N_sample-th step) configurations to rank 0: `cimpc_gather`, NCCL
+            # point-to-point through the C ABI (torch.distributed only handed the 128-byte unique id round)
+            cb.init_comm(im, world, rank)
+            qg = cb.gather_rollouts_capi(im, res_c["q"].permute(1, 0, 2).contiguous(), Rc * world, world, rank)
+            torch.cuda.synchronize()
             gathered = None if qg is None else list(qg.shape)
         else:
             gathered = list(res_c["q"].permute(1, 0, 2).shape)
         closed = {"value": Rc * world * mc.mpc_steps / (float(tc.item()) * 1e-3), "unit": "MPC steps/s (closed loop)",
                   "rollouts_per_gpu": Rc, "sim_steps": H_sim_c, "mpc_steps_per_rollout": mc.mpc_steps,
                   "ms_total": float(tc.item()), "sim_ok_frac": float(okc.item()), "groups": args.closed_loop_groups,
-                  "gathered_trajectory_shape": gathered,
+                  "gathered_trajectory_shape": gathered, "gather": "cimpc_gather (ncclSend/ncclRecv to rank 0)" if dist else "single rank",
                   "config": "examples/quadruped/monte_carlo.jl: initial configurations from the conf_min/conf_max box "
                             "(Philox seed 100), policy every 5 simulator steps, nonlinear simulator step on the device; "
                             "trajectories recorded every 5th step and gathered to rank 0"}

@@ -18,7 +18,10 @@ LIB = os.path.join(LIBDIR, "libcimpc_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("CIMPC_EXTRA_NVCC_FLAGS", "").split()
+if os.environ.get("CIMPC_BUILD_TAG"):  # tuning variants: separate object / library directories
+    BUILD = os.path.join(HERE, "build_" + os.environ["CIMPC_BUILD_TAG"])
+    LIB = os.path.join(LIBDIR, f"libcimpc_b200_{os.environ['CIMPC_BUILD_TAG']}.so")
 
 
 def _sources():

@@ -22,6 +22,7 @@ SYMBOLS = [
     "cimpc_sim_step_batch", "cimpc_linearize", "cimpc_get_linearization",
     "cimpc_newton_create_ex", "cimpc_newton_solve_batch_ex", "cimpc_newton_solve_batch_ex2",
     "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex", "cimpc_newton_create_dense", "cimpc_create_named", "cimpc_ip_solve_batch_host_ex",
+    "cimpc_nccl_get_unique_id", "cimpc_comm_init", "cimpc_gather",
 ]
 
 
@@ -90,6 +91,12 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_ip_solve_batch_host.restype = C.c_int
     lib.cimpc_ip_solve_batch_host_ex.argtypes = [vp, i64, dp, dp, dp, dp, C.POINTER(IPOpts), dp, dp, dp, dp, C.c_uint32]
     lib.cimpc_ip_solve_batch_host_ex.restype = C.c_int
+    lib.cimpc_nccl_get_unique_id.argtypes = [dp]
+    lib.cimpc_nccl_get_unique_id.restype = C.c_int
+    lib.cimpc_comm_init.argtypes = [vp, i32, i32, dp]
+    lib.cimpc_comm_init.restype = C.c_int
+    lib.cimpc_gather.argtypes = [vp, vp, dp, i64, dp, dp, i32, vp]
+    lib.cimpc_gather.restype = C.c_int
     lib.cimpc_launch_count.argtypes = [vp]
     lib.cimpc_launch_count.restype = C.c_int64
     lib.cimpc_newton_opts_default.argtypes = [C.POINTER(NewtonOpts)]

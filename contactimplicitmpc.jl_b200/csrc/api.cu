@@ -1,8 +1,11 @@
 // C ABI (include/cimpc_b200.h): context, linearization upload + set-up kernel, batched solves.
+#include <dlfcn.h>
+
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -345,6 +348,8 @@ struct cimpc_ctx {
   double* dense = nullptr;  // dense linearization arrays of the current reference (see alloc_dense)
   int32_t dense_h = 0;
   bool lin_bad_structure = false;
+  void* nccl_comm = nullptr;  // communicator created by cimpc_comm_init (destroyed with the context)
+  int nccl_world = 1, nccl_rank = 0;
   int* prep_flag = nullptr;  // device int written by prep_kernel (structure check of the uploaded linearization)
 };
 
@@ -480,6 +485,57 @@ static int newton_build_graph(cimpc_ctx* ctx) {
   return CIMPC_OK;
 }
 
+// ---- NCCL, bound at run time -------------------------------------------------------------------------------------
+// The library does not link libnccl: single-GPU users never need it, and a host that already carries an NCCL (CUDA.jl's
+// NCCL.jl artifact, torch's bundled copy) must keep using THAT copy — communicator handles are not portable between two
+// loaded NCCL builds.  So: take the libnccl.so.2 already mapped into the process if there is one, else dlopen it.
+namespace {
+struct NcclApi {
+  struct Id { char b[128]; };  // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed BY VALUE to ncclCommInitRank
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*CommCount)(void*, int*) = nullptr;
+  int (*CommUserRank)(void*, int*) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    auto sym = [&](const char* n) { return dlsym(h, n); };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.CommCount = (decltype(api.CommCount))sym("ncclCommCount");
+    api.CommUserRank = (decltype(api.CommUserRank))sym("ncclCommUserRank");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.CommCount && api.CommUserRank &&
+             api.GroupStart && api.GroupEnd && api.Send && api.Recv;
+  });
+  return api;
+}
+constexpr int NCCL_FLOAT64 = 8;  // ncclDataType_t ncclFloat64 (nccl.h; stable since NCCL 2.0)
+int nccl_fail(cimpc_ctx* c, int rc, const char* where) {
+  NcclApi& a = nccl_api();
+  if (c) c->cuda_err = std::string(where) + ": NCCL " + (a.GetErrorString ? a.GetErrorString(rc) : "error");
+  return CIMPC_ERR_CUDA;
+}
+}  // namespace
+
 extern "C" {
 
 void cimpc_ip_opts_default(cimpc_ip_opts* o) {
@@ -546,6 +602,7 @@ int cimpc_destroy(cimpc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->lin) cudaFree(ctx->lin);
   newton_release(ctx);
+  if (ctx->nccl_comm && nccl_api().ok) nccl_api().CommDestroy(ctx->nccl_comm);
   if (ctx->sim_scratch) cudaFree(ctx->sim_scratch);
   if (ctx->dense) cudaFree(ctx->dense);
   if (ctx->prep_flag) cudaFree(ctx->prep_flag);
@@ -1205,6 +1262,90 @@ int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n, const double* q0, const d
   cudaError_t e = ctx->entry->sim_step(p, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "sim_step_kernel launch");
   ctx->launches++;
+  return CIMPC_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU: final trajectory gather over NCCL (the only collective of the path)
+// ------------------------------------------------------------------------------------------
+int cimpc_nccl_get_unique_id(uint8_t* id128) {
+  if (!id128) return CIMPC_ERR_INVALID_ARGUMENT;
+  NcclApi& a = nccl_api();
+  if (!a.ok) return CIMPC_ERR_NO_DEVICE;
+  return a.GetUniqueId(id128) == 0 ? CIMPC_OK : CIMPC_ERR_CUDA;
+}
+
+int cimpc_comm_init(cimpc_ctx* ctx, int32_t world, int32_t rank, const uint8_t* id128) {
+  if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return CIMPC_ERR_INVALID_ARGUMENT;
+  NcclApi& a = nccl_api();
+  if (!a.ok) {
+    ctx->cuda_err = "libnccl.so.2 not found";
+    return CIMPC_ERR_NO_DEVICE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->nccl_comm) {
+    a.CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  NcclApi::Id id;
+  std::memcpy(id.b, id128, 128);
+  int rc = a.CommInitRank(&ctx->nccl_comm, world, id, rank);
+  if (rc != 0) return nccl_fail(ctx, rc, "ncclCommInitRank");
+  ctx->nccl_world = world;
+  ctx->nccl_rank = rank;
+  return CIMPC_OK;
+}
+
+int cimpc_gather(cimpc_ctx* ctx, void* comm, const double* local, int64_t count, double* out, const int64_t* counts,
+                 int32_t root, void* stream) {
+  if (!ctx || count < 0 || (count > 0 && !local)) return CIMPC_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  NcclApi& a = nccl_api();
+  void* c = comm ? comm : ctx->nccl_comm;
+  int world = 1, rank = 0;
+  if (c) {
+    if (!a.ok) return CIMPC_ERR_NO_DEVICE;
+    int rc = a.CommCount(c, &world);
+    if (rc == 0) rc = a.CommUserRank(c, &rank);
+    if (rc != 0) return nccl_fail(ctx, rc, "ncclCommCount");
+  }
+  if (root < 0 || root >= world) return CIMPC_ERR_INVALID_ARGUMENT;
+  if (world == 1) {  // single rank: the gather is a copy
+    if (!out) return CIMPC_ERR_INVALID_ARGUMENT;
+    if (count > 0 && out != local) CK(cudaMemcpyAsync(out, local, sizeof(double) * count, cudaMemcpyDeviceToDevice, s));
+    return CIMPC_OK;
+  }
+  if (rank == root && !out) return CIMPC_ERR_INVALID_ARGUMENT;
+  // gather-to-root with point-to-point transfers inside one group: the root posts one receive per peer at that
+  // peer's offset (NVLink / NVSwitch carry them concurrently); nobody but the root ever holds the other shards
+  int rc = a.GroupStart();
+  if (rc != 0) return nccl_fail(ctx, rc, "ncclGroupStart");
+  if (rank == root) {
+    int64_t off = 0;
+    for (int r = 0; r < world; ++r) {
+      const int64_t cr = counts ? counts[r] : count;
+      if (cr < 0) { a.GroupEnd(); return CIMPC_ERR_INVALID_ARGUMENT; }
+      if (r == rank) {
+        if (cr != count) { a.GroupEnd(); return CIMPC_ERR_INVALID_ARGUMENT; }
+        if (count > 0 && out + off != local)
+          if (cudaMemcpyAsync(out + off, local, sizeof(double) * count, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+            a.GroupEnd();
+            return cuda_fail(ctx, cudaGetLastError(), "cimpc_gather local copy");
+          }
+      } else if (cr > 0) {
+        rc = a.Recv(out + off, (size_t)cr, NCCL_FLOAT64, r, c, s);
+        if (rc != 0) { a.GroupEnd(); return nccl_fail(ctx, rc, "ncclRecv"); }
+      }
+      off += cr;
+    }
+  } else if (count > 0) {
+    rc = a.Send(local, (size_t)count, NCCL_FLOAT64, root, c, s);
+    if (rc != 0) { a.GroupEnd(); return nccl_fail(ctx, rc, "ncclSend"); }
+  }
+  rc = a.GroupEnd();
+  if (rc != 0) return nccl_fail(ctx, rc, "ncclGroupEnd");
   return CIMPC_OK;
 }
 

@@ -145,8 +145,11 @@ cudaError_t launch_linearize(const LinEvalParams& p, cudaStream_t s) {
 
 // CTA size of ip_solve_kernel.  One-subproblem-per-warp instances (G = 32: centroidal, 74 KB of staged constants) use
 // 512 threads: one CTA per SM either way, but 16 instead of 8 resident warps (the register cap of 128 costs some spills).
+#ifndef CIMPC_IP_THREADS_SHARED
+#define CIMPC_IP_THREADS_SHARED 256  // CTA size of the instances that share a warp between subproblems (G < 32)
+#endif
 template <class D>
-constexpr int ip_threads() { return D::G == 32 ? 512 : 256; }
+constexpr int ip_threads() { return D::G == 32 ? 512 : CIMPC_IP_THREADS_SHARED; }
 
 template <class D>
 LinLayout layout_of() {

@@ -329,6 +329,28 @@ int cimpc_newton_solve_batch_host(cimpc_ctx* ctx, const int32_t* window, const d
 /* `implicit_dynamics!` sweeps (= iterations of the graph's loop) of the last solve; synchronises with the device. */
 int32_t cimpc_newton_last_sweeps(const cimpc_ctx* ctx);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process / context per GPU; rollouts are independent, so the ONLY collective of the path is the final
+ * collection of the trajectories of all runs — `collect_runs`, examples/quadruped/monte_carlo.jl:83-90).  NCCL is bound at
+ * run time (the libnccl.so.2 already loaded by the host — CUDA.jl's NCCL.jl, torch — or the system one); nothing here
+ * needs PyTorch.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* rank 0: 128-byte ncclUniqueId to hand to every rank (Julia: MPI / sockets / a file; `NCCL.UniqueID()` works as well). */
+int cimpc_nccl_get_unique_id(uint8_t* id128);
+/* every rank: create this context's communicator (`ncclCommInitRank`); destroyed with the context. */
+int cimpc_comm_init(cimpc_ctx* ctx, int32_t world, int32_t rank, const uint8_t* id128);
+/*
+ * Gather-to-root of per-rank DEVICE arrays of doubles over NVLink / NVSwitch: rank r contributes `count` doubles
+ * (`counts[r]` on the root; NULL = every rank sends `count`), the root receives them back to back, in rank order, in
+ * `out` (DEVICE, Σ counts doubles; ignored on the other ranks).  `comm`: an `ncclComm_t` of the caller (e.g. NCCL.jl's
+ * `comm.handle`) or NULL for the communicator of cimpc_comm_init.  Point-to-point sends inside one NCCL group: no rank
+ * but the root ever holds another rank's trajectories (an all-gather would ship all of them to everyone).
+ * Asynchronous on `stream`.  With a single rank it is a device copy.
+ */
+int cimpc_gather(cimpc_ctx* ctx, void* comm, const double* local, int64_t count, double* out, const int64_t* counts,
+                 int32_t root, void* stream);
+
 /* Number of kernel launches issued through this context so far (bench bookkeeping). */
 int64_t cimpc_launch_count(const cimpc_ctx* ctx);
 
