@@ -1023,6 +1023,7 @@ static int newton_create_impl(cimpc_ctx* ctx, int32_t H, int64_t R64, const doub
                o_qd = take(sizeof(double) * (obj_qd ? (size_t)H * nq * nq : 1)),
                o_qe = take(sizeof(double) * (obj_qd ? (size_t)H * nq * nq : 1)),
                o_qt = take(sizeof(double) * H * nq), o_vt = take(sizeof(double) * H * nq),
+               o_qi = take(sizeof(double) * H * nq), o_ui = take(sizeof(double) * H * nu),
                o_lsc = take(sizeof(double) * R * lsc);
   CK(cudaMalloc(&nw.arena, off));
   CK(cudaMemset(nw.arena, 0, off));
@@ -1061,6 +1062,15 @@ static int newton_create_impl(cimpc_ctx* ctx, int32_t H, int64_t R64, const doub
   p.kappa = kappa; p.r_tol = nopts->r_tol; p.beta_init = nopts->beta_init; p.max_iter = nopts->max_iter;
   if (obj_q) CK(cudaMemcpy(nw.obj_q, obj_q, sizeof(double) * H * nq, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(nw.obj_u, obj_u, sizeof(double) * H * nu, cudaMemcpyHostToDevice));
+  {  // reciprocal weights (the specialised kernel reads Q⁻¹ from here)
+    std::vector<double> qi((size_t)H * nq, 0.0), ui((size_t)H * nu);
+    if (obj_q)
+      for (int e = 0; e < H * nq; ++e) qi[e] = 1.0 / obj_q[e];
+    for (int e = 0; e < H * nu; ++e) ui[e] = 1.0 / obj_u[e];
+    p.obj_qi = (double*)(b + o_qi); p.obj_ui = (double*)(b + o_ui);
+    CK(cudaMemcpy((void*)p.obj_qi, qi.data(), sizeof(double) * H * nq, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((void*)p.obj_ui, ui.data(), sizeof(double) * H * nu, cudaMemcpyHostToDevice));
+  }
   if (obj_qd) {
     p.obj_qd = (double*)(b + o_qd); p.obj_e = (double*)(b + o_qe);
     CK(cudaMemcpy((void*)p.obj_qd, obj_qd, sizeof(double) * (size_t)H * nq * nq, cudaMemcpyHostToDevice));
