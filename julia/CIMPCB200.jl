@@ -241,4 +241,70 @@ function policy!(b::B200ImplicitTrajectory, p::CI.CIMPC, q0_dev, q_tp1, u_out, t
     return u_out
 end
 
+# ---------------------------------------------------------------------------------------------------------------
+# Round-2 entry points (all declared in include/cimpc_b200.h; NOT executed here either — no Julia in the image)
+# ---------------------------------------------------------------------------------------------------------------
+
+"""`get_simulation(name, …; model_variable_name = "quadruped_payload")`: a context whose generated residual is the named
+model's (examples/quadruped/payload.jl:10-14) — used for the simulated plant and for device-side linearization."""
+function create_named(desc::ModelDesc, model_name::String; device = 0)
+    ctx = Ref{Ptr{Cvoid}}()
+    check(C_NULL, ccall((:cimpc_create_named, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ref{ModelDesc}, Cstring),
+        ctx, device, Ref(desc), model_name))
+    return ctx[]
+end
+
+"""`Newton(...; obj)` with full matrices `obj.q[t]` (`relative_state_cost`, centroidal_quadruped/model.jl:168-183) and the
+`v_target` of a `TrackingVelocityObjective` (objective.jl:18-47); :configuration mode."""
+function newton_create_dense!(b::B200ImplicitTrajectory, H_mpc::Int, R::Int, obj, κ::Float64, nopts::CI.NewtonOptions)
+    obj_q = cat((Matrix{Float64}(obj.q[t]) for t in 1:H_mpc)...; dims = 3)          # nq × nq × H_mpc
+    obj_u = hcat((diag(obj.u[t]) for t in 1:H_mpc)...)
+    vel = obj isa CI.TrackingVelocityObjective
+    obj_v = vel ? hcat((diag(obj.v[t]) for t in 1:H_mpc)...) : nothing
+    v_tgt = vel ? hcat((Vector{Float64}(obj.v_target[t]) for t in 1:H_mpc)...) : nothing
+    no = Ref(NewtonOpts(nopts.r_tol, nopts.β_init, nopts.max_iter, 0))
+    GC.@preserve obj_q obj_u obj_v v_tgt check(b.ctx, ccall((:cimpc_newton_create_dense, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{NewtonOpts}, Ref{IPOpts}),
+        b.ctx, H_mpc, R, obj_q, obj_u, vel ? pointer(obj_v) : C_NULL, vel ? pointer(v_tgt) : C_NULL, κ, no, Ref(b.opts)))
+end
+
+"""One MPC step of every rollout with HOST arrays — what `policy(p, traj, t)` exchanges with its caller
+(policy.jl:118-120, 141-144): `q0`, `q1` nq × R in, `u` nu × R out; `alt` nc × R = every rollout's `p.altitude`."""
+function newton_solve_host!(b::B200ImplicitTrajectory, p::CI.CIMPC, q0::Matrix{Float64}, q1::Matrix{Float64},
+        u_out::Matrix{Float64}; active = nothing, alt = nothing, warm_start = true, info = nothing, μ, h)
+    H = p.newton.H
+    window = Int32.(p.window .- 1)
+    ref_q = hcat(p.traj.q[1:H+2]...); ref_u = hcat(p.traj.u[1:H]...)
+    ref_γ = hcat(p.traj.γ[1:H]...); ref_b = hcat(p.traj.b[1:H]...)
+    check(b.ctx, ccall((:cimpc_newton_solve_batch_host, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64},
+         Ptr{Float64}, Ptr{UInt8}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Int32}),
+        b.ctx, window, ref_q, ref_u, ref_γ, ref_b, μ, h, q0, q1, active === nothing ? C_NULL : active,
+        alt === nothing ? C_NULL : alt, warm_start, u_out, info === nothing ? C_NULL : info))
+end
+
+"""`update_altitude!` (mpc_utils.jl:109-135) for R rollouts on the host: `γ_hist` nc × N_sample × R and `ϕ_hist` of the same
+shape are the normal impulses and signed distances (the `phi` output of `cimpc_sim_step_batch_ex`) of the last
+N_sample simulator steps."""
+function update_altitude!(alt::Matrix{Float64}, γ_hist::Array{Float64,3}, ϕ_hist::Array{Float64,3}; threshold = 1.0)
+    nc, _, R = size(γ_hist)
+    for r in 1:R, i in 1:nc
+        γmax, j = findmax(@view γ_hist[i, :, r])
+        γmax > threshold && (alt[i, r] = ϕ_hist[i, j, r])
+    end
+    return alt
+end
+
+"""The only collective of the path: gather every rank's trajectories on `root` (`collect_runs`,
+examples/quadruped/monte_carlo.jl:83-90).  `comm` = an `ncclComm_t` (NCCL.jl: `comm.handle`), or C_NULL after `comm_init!`."""
+function gather!(b::B200ImplicitTrajectory, out, loc, counts::Vector{Int64}; comm = C_NULL, root = 0, stream = C_NULL)
+    check(b.ctx, ccall((:cimpc_gather, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Int64}, Int32, Ptr{Cvoid}),
+        b.ctx, comm, loc, length(loc), out, counts, root, stream))
+end
+nccl_unique_id() = (id = zeros(UInt8, 128); check(C_NULL, ccall((:cimpc_nccl_get_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)
+comm_init!(b::B200ImplicitTrajectory, world::Int, rank::Int, id::Vector{UInt8}) =
+    check(b.ctx, ccall((:cimpc_comm_init, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), b.ctx, world, rank, id))
+
+
 end # module

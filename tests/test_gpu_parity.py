@@ -118,6 +118,52 @@ def test_reference_settings_parity(cuda_device, robot, mode, kw):
     assert (rv[st] < opts.r_tol + 1e-11).all() and (kv[st] < opts.kappa_tol * (1 + 1e-9)).all()
 
 
+def test_mismatch_rate_at_bench_settings_full_batch(cuda_device):
+    """SURVEY §8c asks for the mismatch RATE, measured and recorded, at the bench's own settings: quadruped, r_tol =
+    κ_tol = 1e-4, max_ls = 3 (the reference's back-tracking, whose acceptance test compares round-off-level numbers),
+    the full 655 360-subproblem sweep of BASELINE config 4 against the C oracle with LU-accurate solves.  Recorded in
+    gpurun_out/r02_mismatch_rate.json (copied to profiles/).  Also exercises the output mask: only z and the status
+    cross the bus."""
+    import json
+    import os
+    import cimpc_b200 as cb
+    robot, mode = "quadruped", "configuration"
+    lin, gait = load_lin(robot), load_gait(robot)
+    R, H = 65536, 10
+    n = R * H
+    knot, theta, q2 = make_batch(robot, lin, gait, n, seed=100)
+    nq = SIZES[robot][0]
+    stage = (np.arange(n) // R).astype(np.int32)
+    theta = np.ascontiguousarray(theta - lin["th0"][knot] + lin["th0"][stage])
+    q2 = np.ascontiguousarray(q2 - lin["z0"][knot, :nq] + lin["z0"][stage, :nq])
+    opts = cb.InteriorPointOptions(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, diff_sol=False)  # max_ls = 3
+    im = _ctx(robot, lin, mode, opts)
+    z = np.zeros((n, im.nz)); st = np.zeros(n, np.uint8); it = np.zeros(n, np.int32)
+    im.solve_host_into(stage, theta, q2, None, z, None, st, it, out_mask=im.OUT_Z | im.OUT_STATUS)
+    zo, _, sto, ito = _c_oracle(robot, lin, mode, "lu").solve(stage, theta, q2, _oracle_opts(opts))
+    st = st.astype(bool)
+    ez = np.abs(z - zo).max(axis=1) / np.maximum(1.0, np.abs(zo).max(axis=1))
+    same_it = it == ito
+    agree = same_it & (ez <= 1e-9) & (st == sto)
+    rec = {"workload": "BASELINE config 4 sweep: quadruped, 655360 subproblems, r_tol = kappa_tol = 1e-4, max_ls = 3",
+           "status_mismatches": int((st != sto).sum()), "converged_frac_gpu": float(st.mean()),
+           "iteration_count_mismatch_rate": float(1.0 - same_it.mean()),
+           "z_mismatch_rate_1e-9": float(1.0 - agree.mean()),
+           "max_rel_z_error_where_iterations_agree": float(ez[same_it].max()),
+           "median_rel_z_error": float(np.median(ez)),
+           "mean_iterations_gpu": float(it.mean()), "mean_iterations_oracle": float(ito.mean())}
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "r02_mismatch_rate.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+    print(rec)
+    assert rec["status_mismatches"] == 0 and st.all()
+    assert agree.mean() >= 0.97, rec
+    # every returned point satisfies the stopping criteria on the independently recomputed residual (a 1/64 sample)
+    sel = np.arange(0, n, 64)
+    rv, kv = independent_violation(robot, lin, stage[sel], theta[sel], z[sel])
+    assert (rv < 1e-4 + 1e-11).all() and (kv < 1e-4 * (1 + 1e-9)).all()
+
+
 def test_host_and_device_entry_points_agree(cuda_device):
     import torch
     import cimpc_b200 as cb
