@@ -1024,6 +1024,7 @@ static int newton_create_impl(cimpc_ctx* ctx, int32_t H, int64_t R64, const doub
                o_qe = take(sizeof(double) * (obj_qd ? (size_t)H * nq * nq : 1)),
                o_qt = take(sizeof(double) * H * nq), o_vt = take(sizeof(double) * H * nq),
                o_qi = take(sizeof(double) * H * nq), o_ui = take(sizeof(double) * H * nu),
+               o_qsi = take(sizeof(double) * H * nq), o_usi = take(sizeof(double) * H * nu),
                o_lsc = take(sizeof(double) * R * lsc);
   CK(cudaMalloc(&nw.arena, off));
   CK(cudaMemset(nw.arena, 0, off));
@@ -1070,6 +1071,11 @@ static int newton_create_impl(cimpc_ctx* ctx, int32_t H, int64_t R64, const doub
     p.obj_qi = (double*)(b + o_qi); p.obj_ui = (double*)(b + o_ui);
     CK(cudaMemcpy((void*)p.obj_qi, qi.data(), sizeof(double) * H * nq, cudaMemcpyHostToDevice));
     CK(cudaMemcpy((void*)p.obj_ui, ui.data(), sizeof(double) * H * nu, cudaMemcpyHostToDevice));
+    for (double& v : qi) v = std::sqrt(v);
+    for (double& v : ui) v = std::sqrt(v);
+    p.obj_qsi = (double*)(b + o_qsi); p.obj_usi = (double*)(b + o_usi);
+    CK(cudaMemcpy((void*)p.obj_qsi, qi.data(), sizeof(double) * H * nq, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((void*)p.obj_usi, ui.data(), sizeof(double) * H * nu, cudaMemcpyHostToDevice));
   }
   if (obj_qd) {
     p.obj_qd = (double*)(b + o_qd); p.obj_e = (double*)(b + o_qe);

@@ -87,6 +87,8 @@ struct NewtonParams {
   // dense-weight variant only (newton_dense.cuh)
   const double* obj_qi = nullptr;               // H×nq    1 / obj_q   (specialised kernel)
   const double* obj_ui = nullptr;               // H×nu    1 / obj_u
+  const double* obj_qsi = nullptr;              // H×nq    √(1 / obj_q)  (newton_cta.cuh)
+  const double* obj_usi = nullptr;              // H×nu    √(1 / obj_u)
   const double* obj_qd = nullptr;               // H×nq×nq column-major  obj.q[t]
   const double* obj_e = nullptr;                // H×nq×nq column-major  E_t = L_t⁻ᵀ, obj.q[t] = L_t L_tᵀ
   const double* q_tgt = nullptr;                // H×nq    obj.q_target (null: zeros)

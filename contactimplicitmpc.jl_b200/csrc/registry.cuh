@@ -2,11 +2,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "ip_kernel.cuh"
 #include "lin_kernel.cuh"
 #include "newton_kernel.cuh"
+#include "newton_cta.cuh"
 #include "newton_general.cuh"
 #include "newton_dense.cuh"
 #include "sim_kernel.cuh"
@@ -72,8 +74,28 @@ cudaError_t launch_newton_reset(const NewtonParams& p, const NewtonCall* call, c
   return cudaGetLastError();
 }
 
+// CIMPC_NEWTON_KERNEL=warp selects the round-1 warp-per-rollout kernel (A/B measurements; same arithmetic up to the
+// summation order of the residual's δzᵀν terms).
+inline bool newton_use_cta_kernel() {
+  static const bool cta = [] {
+    const char* v = getenv("CIMPC_NEWTON_KERNEL");
+    return !(v && v[0] == 'w');
+  }();
+  return cta;
+}
+
 template <class D>
 cudaError_t launch_newton_step(const NewtonParams& p, double* lscratch, cudaStream_t s) {
+  if constexpr (NewtonCtaSmem<D>::SUPPORTED) {
+    // one CTA per rollout with all of its δz in shared memory; longer horizons take the warp-per-rollout kernel below
+    const size_t cbytes = (size_t)NewtonCtaSmem<D>::doubles(p.H) * sizeof(double);
+    if (newton_use_cta_kernel() && cbytes <= NEWTON_CTA_MAX_SMEM) {
+      static SmemOptIn copt;
+      if (cudaError_t e = copt.ensure(newton_step_cta_kernel<D>, cbytes); e != cudaSuccess) return e;
+      newton_step_cta_kernel<D><<<p.R, NEWTON_CTA_THREADS, cbytes, s>>>(p, lscratch);
+      return cudaGetLastError();
+    }
+  }
   const size_t bytes = (size_t)NewtonSmem<D>::per_warp(p.H) * NEWTON_WARPS * sizeof(double);
   static SmemOptIn opt;
   if (cudaError_t e = opt.ensure(newton_step_kernel<D, NEWTON_THREADS>, bytes); e != cudaSuccess) return e;
