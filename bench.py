@@ -511,7 +511,8 @@ def main():
         q0m = torch.from_numpy(np.tile(gait["q"][0], (Rm, 1))).to(dev)
         q1m = torch.from_numpy(gait["q"][1] + 0.01 * rng.standard_normal((Rm, nq))).to(dev)
         win = np.arange(H_MPC + 2, dtype=np.int32)
-        newton.solve(win, gait["q"][:H_MPC + 2], gait["u"][:H_MPC], gait["mu"], gait["h"], q0m, q1m)
+        for _ in range(2):  # warm-up (graph instantiation, lazy module loading)
+            newton.solve(win, gait["q"][:H_MPC + 2], gait["u"][:H_MPC], gait["mu"], gait["h"], q0m, q1m)
         torch.cuda.synchronize()
         if dist:
             dist.barrier()

@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(NEWTON_CTA_THREADS, NEWTON_CTA_MIN_CTAS) newto
     double *ZZ0 = blk + 6 * BS, *ZZ1 = blk + 7 * BS;
     // work items of a block column: NTRI lower-triangular entries of the diagonal block, then the BS entries of the first
     // sub-diagonal block
-    auto item_rc = [&](int it, int& a, int& b) {
+    auto item_rc = [&](int it) -> int {  // (a, b) packed as a | b << 8
+      int a, b;
       if (it < NTRI) {
         b = 0;
         int rem = it;
@@ -240,37 +241,43 @@ __global__ void __launch_bounds__(NEWTON_CTA_THREADS, NEWTON_CTA_MIN_CTAS) newto
         a = (it - NTRI) % ND;
         b = (it - NTRI) / ND;
       }
+      return a | (b << 8);
     };
-    // ZZ0 = Z̃_t Z̃_tᵀ + Qq_t⁻¹ + ρI (lower triangle);  ZZ1 = −δq1_{t+1} Qq_t⁻¹ + Z̃q0_{t+1} Z̃q1_tᵀ
-    auto zz_items = [&](int t, int first, int stride) {
-      for (int it = first; it < NTRI + BS; it += stride) {
-        int a, b;
-        item_rc(it, a, b);
-        if (it < NTRI) {
-          double acc = (a == b) ? QIq(t, a) + rho : 0.0;
-          const double* za = zall + t * ZB + a;
-          const double* zb = zall + t * ZB + b;
-#pragma unroll 6
-          for (int c = 0; c < NCOL; ++c) acc = fma(za[c * ND], zb[c * ND], acc);
-          ZZ0[a + b * ND] = acc;
-        } else if (t + 1 < H) {
-          double c1 = -Z(t + 1, NQ + b, a) * SQq(t, b);
-          const double* za = zall + (t + 1) * ZB + a;
-          const double* zb = zall + t * ZB + NQ * ND + b;
+    // the items of this thread in the two mappings (all 128 threads / warps 1–3), decoded once
+    constexpr int NIT = (NTRI + BS + T - 1) / T, NIT3 = (NTRI + BS + T - 33) / (T - 32);
+    int ab_all[NIT], ab_w13[NIT3];
 #pragma unroll
-          for (int k = 0; k < NQ; ++k) c1 = fma(za[k * ND], zb[k * ND], c1);
-          ZZ1[a + b * ND] = c1;
-        }
+    for (int k = 0; k < NIT; ++k) ab_all[k] = item_rc(tid + k * T);
+#pragma unroll
+    for (int k = 0; k < NIT3; ++k) ab_w13[k] = item_rc((tid >= 32 ? tid - 32 : tid) + k * (T - 32));
+    // ZZ0 = Z̃_t Z̃_tᵀ + Qq_t⁻¹ + ρI (lower triangle);  ZZ1 = −δq1_{t+1} Qq_t⁻¹ + Z̃q0_{t+1} Z̃q1_tᵀ
+    auto zz_item = [&](int t, int it, int ab) {
+      const int a = ab & 255, b = ab >> 8;
+      if (it < NTRI) {
+        double acc = (a == b) ? QIq(t, a) + rho : 0.0;
+        const double* za = zall + t * ZB + a;
+        const double* zb = zall + t * ZB + b;
+#pragma unroll 6
+        for (int c = 0; c < NCOL; ++c) acc = fma(za[c * ND], zb[c * ND], acc);
+        ZZ0[a + b * ND] = acc;
+      } else if (it < NTRI + BS && t + 1 < H) {
+        double c1 = -Z(t + 1, NQ + b, a) * SQq(t, b);
+        const double* za = zall + (t + 1) * ZB + a;
+        const double* zb = zall + t * ZB + NQ * ND + b;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) c1 = fma(za[k * ND], zb[k * ND], c1);
+        ZZ1[a + b * ND] = c1;
       }
     };
-    zz_items(0, tid, T);
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) zz_item(0, tid + k * T, ab_all[k]);
     __syncthreads();
     for (int t = 0; t < H; ++t) {
       // ---- phase A (all threads): block column t = factor-independent part − pending Cholesky updates; the two
       //      sub-diagonal blocks of column t−1 (now P1, P2) go to the scratch for the backward pass ----
-      for (int it = tid; it < NTRI + BS; it += T) {
-        int a, b;
-        item_rc(it, a, b);
+#pragma unroll
+      for (int kk = 0; kk < NIT; ++kk) {
+        const int it = tid + kk * T, a = ab_all[kk] & 255, b = ab_all[kk] >> 8;
         if (it < NTRI) {
           double acc = ZZ0[a + b * ND];
           if (t >= 1)
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(NEWTON_CTA_THREADS, NEWTON_CTA_MIN_CTAS) newto
           if (t >= 2)
             for (int k = 0; k < ND; ++k) acc = fma(-Q2[a + k * ND], Q2[b + k * ND], acc);
           A0[a + b * ND] = acc;
-        } else if (t + 1 < H) {
+        } else if (it < NTRI + BS && t + 1 < H) {
           double c1 = ZZ1[a + b * ND];
           if (t >= 1)
             for (int k = 0; k < ND; ++k) c1 = fma(-P2[a + k * ND], P1[b + k * ND], c1);
@@ -315,7 +322,8 @@ __global__ void __launch_bounds__(NEWTON_CTA_THREADS, NEWTON_CTA_MIN_CTAS) newto
         for (int c = 0; c < ND; ++c)
           if (lane < ND && c <= lane) A0[lane + c * ND] = rw[c];
       } else if (t + 1 < H) {
-        zz_items(t + 1, tid - 32, T - 32);
+#pragma unroll
+        for (int k = 0; k < NIT3; ++k) zz_item(t + 1, tid - 32 + k * (T - 32), ab_w13[k]);
       }
       __syncthreads();
       // ---- phase C: warps 1, 2: trsm  [A1; A2] ← [A1; A2] L⁻ᵀ (one row per lane, the row in registers; the (t+2,t)
