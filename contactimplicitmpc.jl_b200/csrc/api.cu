@@ -386,6 +386,7 @@ static void newton_release(cimpc_ctx* ctx) {
 static const ModelEntry* find_entry(const cimpc_model_desc& d, const char* model_name) {
   std::string want = model_name ? model_name : "";
   if (want == "hopper_2D") want = "hopper2d";
+  if (want == "hopper_2D_piecewise") want = "hopper2d_piecewise";
   if (want == "centroidal_quadruped") want = "centroidal";
   if (want == "centroidal_quadruped_payload") want = "centroidal_payload";
 #define CIMPC_SEARCH(tag_, nq, nu, nw, nc, nb)                                                   \

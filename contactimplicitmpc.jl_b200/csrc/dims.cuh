@@ -97,12 +97,17 @@ struct Dims {
 //                         nq  nu nw nc nb
 // The *_payload entries share the sizes (and therefore the solver kernels) of their nominal robot; what differs is the
 // generated residual used by the simulator step and the device linearization (cimpc_create_named selects them).
+// The *_piecewise entries are the planar robots on the terrain `piecewise1_2D_lc` (get_simulation(robot,
+// "piecewise1_2D_lc", "piecewise", approx = true)): the generated residual evaluates the surface under every contact.
 #define CIMPC_FOR_EACH_MODEL(X)        \
   X(hopper2d, 4, 2, 2, 1, 2)           \
   X(quadruped, 11, 8, 2, 4, 8)         \
   X(flamingo, 9, 6, 2, 4, 8)           \
   X(centroidal, 18, 12, 3, 4, 16)      \
   X(quadruped_payload, 11, 8, 2, 4, 8) \
-  X(centroidal_payload, 18, 12, 3, 4, 16)
+  X(centroidal_payload, 18, 12, 3, 4, 16) \
+  X(hopper2d_piecewise, 4, 2, 2, 1, 2) \
+  X(flamingo_piecewise, 9, 6, 2, 4, 8) \
+  X(quadruped_piecewise, 11, 8, 2, 4, 8)
 
 }  // namespace cimpc

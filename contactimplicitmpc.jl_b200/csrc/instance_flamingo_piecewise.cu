@@ -1,0 +1,8 @@
+// Kernel instances for a planar robot on the piecewise terrain (src/simulation/environments/piecewise.jl): same sizes as
+// the robot on flat ground (the solver kernels are the base robot's, taken from its entries), its own
+// generated residual with the terrain atoms.
+#include "gen/residual_flamingo_piecewise.h"
+#include "registry.cuh"
+namespace cimpc {
+CIMPC_DEFINE_VARIANT_ENTRIES(flamingo_piecewise, flamingo, 9, 6, 2, 4, 8)
+}

@@ -39,12 +39,25 @@ __global__ void __launch_bounds__(GEN::NS * 32) linearize_kernel(const LinEvalPa
   auto th = [&](int i) { return tt[i]; };
   auto tr = [&](int i) { return trig[i * 32 + lane]; };
   for (int k = wid; k < NTRIG; k += WARPS) {
+    if (GEN::is_terr(k)) continue;
     double sn, cs;
     sincos(GEN::trig_arg(k, z, th), &sn, &cs);
     trig[(2 * k) * 32 + lane] = sn;
     trig[(2 * k + 1) * 32 + lane] = cs;
   }
   __syncthreads();
+  if constexpr (GEN::NTERR > 0) {  // terrain atoms: surface height, slope and rotation under every contact point
+    for (int i = wid; i < GEN::NTERR; i += WARPS) {
+      const double x = GEN::terr_x(i, z, th, tr);
+      double f, g, c, sn;
+      GEN::terr_atoms(x, f, g, c, sn);
+      trig[(2 * (GEN::TERR0 + 2 * i)) * 32 + lane] = f;
+      trig[(2 * (GEN::TERR0 + 2 * i) + 1) * 32 + lane] = g;
+      trig[(2 * (GEN::TERR0 + 2 * i + 1)) * 32 + lane] = c;
+      trig[(2 * (GEN::TERR0 + 2 * i + 1) + 1) * 32 + lane] = sn;
+    }
+    __syncthreads();
+  }
   if (!valid) return;
   double* r0 = p.r0 + (size_t)t * NZ;
   double* rz = p.rz0 + (size_t)t * NZ * NZ;

@@ -247,4 +247,27 @@ CIMPC_FOR_EACH_MODEL(CIMPC_DECLARE_ENTRY)
     return e;                                                                                     \
   }
 
+// A variant of a robot (payload, terrain): the solver kernels of the base robot (same sizes: the SAME instantiations, not
+// compiled a second time) with the variant's own generated residual behind the simulator step and the linearization.
+#define CIMPC_DEFINE_VARIANT_ENTRIES(name_, base_, nq, nu, nw, nc, nb)                            \
+  const ModelEntry* entries_##name_(int* count) {                                                 \
+    using GEN = gen_##name_::Gen;                                                                 \
+    static_assert(GEN::NQ == nq && GEN::NU == nu && GEN::NW == nw && GEN::NC == nc && GEN::NB == nb, "generated model"); \
+    static ModelEntry e[2];                                                                       \
+    static std::once_flag once;                                                                   \
+    std::call_once(once, [] {                                                                     \
+      int c = 0;                                                                                  \
+      const ModelEntry* b = entries_##base_(&c);                                                  \
+      for (int i = 0; i < 2; ++i) {                                                               \
+        e[i] = b[i];                                                                              \
+        e[i].name = #name_;                                                                       \
+        e[i].sim_step = &launch_sim_step<GEN>;                                                    \
+        e[i].sim_scratch = &sim_scratch_doubles<GEN>;                                             \
+        e[i].linearize = &launch_linearize<GEN>;                                                  \
+      }                                                                                           \
+    });                                                                                           \
+    *count = 2;                                                                                   \
+    return e;                                                                                     \
+  }
+
 }  // namespace cimpc

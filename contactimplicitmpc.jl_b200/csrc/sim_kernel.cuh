@@ -45,7 +45,7 @@ struct SimParams {
   double* q2_out;     // nq × R   q_{t+2}
   double* gamma_out;  // nc × R
   double* b_out;      // nb × R
-  double* phi_out;    // nc × R or null: s1 = ϕ(q_{t+2}) of the solution (signed distances, for `update_altitude!`)
+  double* phi_out;    // nc × R or null: ϕ(q_{t+2}) of the solution over FLAT ground (contact-point heights, for `update_altitude!`)
   uint8_t* status;    // R
   int32_t* iters;     // R
   double* scratch;    // per tile of 32 rollouts: SimLayout::TILE × 32 doubles
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
         // trig atoms of the candidate point (the θ-only ones once per rollout, on trip 0)
         if (ev) {
           for (int k = wid; k < (it == 0 ? L::NTRIG : L::NTRIG_VAR); k += WARPS) {
+            if (GEN::is_terr(k)) continue;
             double sn, cs;
             sincos(GEN::trig_arg(k, zc, thc), &sn, &cs);
             S(o_tr, 2 * k) = sn;
@@ -298,6 +299,20 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
           }
         }
         __syncthreads();
+        if constexpr (GEN::NTERR > 0) {  // terrain atoms: surface height, slope and rotation under every contact point
+          if (ev) {
+            for (int i = wid; i < GEN::NTERR; i += WARPS) {
+              const double x = GEN::terr_x(i, zc, thc, trc);
+              double f, g, c, sn;
+              GEN::terr_atoms(x, f, g, c, sn);
+              S(o_tr, 2 * (GEN::TERR0 + 2 * i)) = f;
+              S(o_tr, 2 * (GEN::TERR0 + 2 * i) + 1) = g;
+              S(o_tr, 2 * (GEN::TERR0 + 2 * i + 1)) = c;
+              S(o_tr, 2 * (GEN::TERR0 + 2 * i + 1) + 1) = sn;
+            }
+          }
+          __syncthreads();
+        }
         double rv = 0.0, kv = 0.0;
         if (ev) {
           GEN::r_slice(wid, zc, thc, trc, 0.0, [&](int i, double v) {
@@ -516,7 +531,13 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
     for (int e = 0; e < NC; ++e) p.gamma_out[(size_t)rr * NC + e] = S(L::O_Z, NQ + e);
     for (int e = 0; e < NB; ++e) p.b_out[(size_t)rr * NB + e] = S(L::O_Z, NQ + NC + e);
     if (p.phi_out != nullptr)
-      for (int e = 0; e < NC; ++e) p.phi_out[(size_t)rr * NC + e] = S(L::O_Z, NQ + 2 * NC + NB + e);
+      for (int e = 0; e < NC; ++e) {
+        // on a terrain s1 is the distance to the surface; `update_altitude!` evaluates ϕ of the POLICY's flat-ground model
+        // (mpc_utils.jl:127: ϕ_func(s.model, s.env, q)), i.e. the height of the contact point: s1 + surface height
+        double v = S(L::O_Z, NQ + 2 * NC + NB + e);
+        if constexpr (GEN::NTERR > 0) v += S(L::O_TR, 2 * (GEN::TERR0 + 2 * e));
+        p.phi_out[(size_t)rr * NC + e] = v;
+      }
   }
 }
 

@@ -36,17 +36,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 if __package__ in (None, ""):
     sys.path.insert(0, os.path.dirname(HERE))
     from modelgen.robots import get_model  # type: ignore
-    from modelgen.symbolic import symbolic_residual  # type: ignore
+    from modelgen.symbolic import symbolic_residual_env  # type: ignore
+    from modelgen.terrain import get_terrain  # type: ignore
 else:
     from .robots import get_model
-    from .symbolic import symbolic_residual
+    from .symbolic import symbolic_residual_env
+    from .terrain import get_terrain
 
 GEN_DIR = os.path.join(os.path.dirname(HERE), "csrc", "gen")
 ROBOTS = {"hopper_2D": "hopper2d", "quadruped": "quadruped", "flamingo": "flamingo",
           "centroidal_quadruped": "centroidal",
           # payload variants: same sizes and kernels, other inertial parameters (examples/quadruped/payload.jl simulates
           # `quadruped_payload` under a policy built on the nominal model; BASELINE config 5 asks for the centroidal analogue)
-          "quadruped_payload": "quadruped_payload", "centroidal_quadruped_payload": "centroidal_payload"}
+          "quadruped_payload": "quadruped_payload", "centroidal_quadruped_payload": "centroidal_payload",
+          # planar robots on the piecewise terrain (get_simulation(robot, "piecewise1_2D_lc", "piecewise", approx = true),
+          # examples/hopper/piecewise.jl:11, examples/flamingo/piecewise.jl:11, examples/quadruped/piecewise.jl:11)
+          "hopper_2D_piecewise": "hopper2d_piecewise", "flamingo_piecewise": "flamingo_piecewise",
+          "quadruped_piecewise": "quadruped_piecewise"}
 
 
 class _Printer(C99CodePrinter):
@@ -77,8 +83,10 @@ def _deal(costs, ns=NS):
     return [sorted(b) for b in bins]
 
 
-def _hoist_trig(exprs, z):
-    """Replace sin(a)/cos(a) by symbols sn<k>/cs<k>; returns (new exprs, [arguments], #z-dependent)."""
+def _hoist_trig(exprs, z, n_terr=0):
+    """Replace sin(a)/cos(a) by symbols sn<k>/cs<k>; returns (new exprs, [arguments], #z-dependent).
+    `n_terr` terrain contacts reserve 2·n_terr atoms (argument 0) right after the z-dependent trig atoms: atom
+    T0 + 2i holds (height, slope) under contact i, atom T0 + 2i + 1 (cos, sin) of its surface rotation."""
     args = set()
     for e in exprs:
         for a in e.atoms(sp.sin, sp.cos):
@@ -86,18 +94,20 @@ def _hoist_trig(exprs, z):
     zs = set(z)
     var = sorted((a for a in args if a.free_symbols & zs), key=sp.default_sort_key)
     const = sorted((a for a in args if not (a.free_symbols & zs)), key=sp.default_sort_key)
-    order = var + const
+    order = var + [sp.Integer(0)] * (2 * n_terr) + const
     sub = {}
     for k, a in enumerate(order):
+        if len(var) <= k < len(var) + 2 * n_terr:
+            continue
         sub[sp.sin(a)] = sp.Symbol(f"sn{k}", real=True)
         sub[sp.cos(a)] = sp.Symbol(f"cs{k}", real=True)
     out = [e.xreplace(sub) for e in exprs]
     for e in out:
         assert not e.atoms(sp.sin, sp.cos), "unhoisted trigonometric atom"
-    return out, order, len(var)
+    return out, order, len(var) + 2 * n_terr
 
 
-def _emit(exprs, idx, out_fmt, z, th, pr, ntrig=0):
+def _emit(exprs, idx, out_fmt, z, th, pr, ntrig=0, terr0=0, n_terr=0):
     """Straight-line code for the outputs `idx` of `exprs` (own CSE)."""
     if not idx:
         return [], 0
@@ -120,6 +130,11 @@ def _emit(exprs, idx, out_fmt, z, th, pr, ntrig=0):
             lines.append(f"  const double sn{k} = tr({2 * k});")
         if f"cs{k}" in names:
             lines.append(f"  const double cs{k} = tr({2 * k + 1});")
+    for i in range(n_terr):
+        for nm, slot in ((f"tf{i}", 2 * (terr0 + 2 * i)), (f"tg{i}", 2 * (terr0 + 2 * i) + 1),
+                         (f"tc{i}", 2 * (terr0 + 2 * i + 1)), (f"ts{i}", 2 * (terr0 + 2 * i + 1) + 1)):
+            if nm in names:
+                lines.append(f"  const double {nm} = tr({slot});")
     for s, e in repl:
         lines.append(f"  const double {s} = {pr.doprint(e)};")
     for k, e in zip(idx, red):
@@ -129,24 +144,32 @@ def _emit(exprs, idx, out_fmt, z, th, pr, ntrig=0):
 
 def generate(robot: str) -> str:
     m = get_model(robot)
-    z, th, kappa, r = symbolic_residual(m)
+    z, th, kappa, r, r_diff, terr = symbolic_residual_env(m)
+    n_terr = m.nc if terr else 0
     pr = _Printer()
-    rvec = sp.Matrix(r)
+    rvec = sp.Matrix(r_diff)  # = r on flat ground; on a terrain the surface enters as its tangent line (symbolic.py)
     J = rvec.jacobian(sp.Matrix(z))
     nnz = [(i, j) for j in range(m.nz) for i in range(m.nz) if J[i, j] != 0]  # column-major order
     Jt = rvec.jacobian(sp.Matrix(th))
     nnzt = [(i, j) for j in range(m.ntheta) for i in range(m.nz) if Jt[i, j] != 0]
-    hoisted, trig_args, ntv = _hoist_trig(list(r) + [J[i, j] for i, j in nnz] + [Jt[i, j] for i, j in nnzt], z)
+    px = list(terr["px"]) if terr else []
+    hoisted, trig_args, ntv = _hoist_trig(list(r) + [J[i, j] for i, j in nnz] + [Jt[i, j] for i, j in nnzt] + px, z, n_terr)
     nt = len(trig_args)
+    terr0 = ntv - 2 * n_terr
+    if terr:
+        px_h = hoisted[len(hoisted) - n_terr:]
+        hoisted = hoisted[:len(hoisted) - n_terr]
+        for e in hoisted:
+            assert not (e.free_symbols & set(terr["x0"])), "expansion point left in an output"
     r_exprs = hoisted[:m.nz]
     j_exprs = hoisted[m.nz:m.nz + len(nnz)]
     t_exprs = hoisted[m.nz + len(nnz):]
     r_bins = _deal([sp.count_ops(e) + 1 for e in r_exprs])
     j_bins = _deal([sp.count_ops(e) + 1 for e in j_exprs])
-    r_sl = [_emit(r_exprs, b, "r({i}, {e});", z, th, pr, nt) for b in r_bins]
-    j_sl = [_emit(j_exprs, b, "J({i}, {e});", z, th, pr, nt) for b in j_bins]
+    r_sl = [_emit(r_exprs, b, "r({i}, {e});", z, th, pr, nt, terr0, n_terr) for b in r_bins]
+    j_sl = [_emit(j_exprs, b, "J({i}, {e});", z, th, pr, nt, terr0, n_terr) for b in j_bins]
     t_bins = _deal([sp.count_ops(e) + 1 for e in t_exprs])
-    t_sl = [_emit(t_exprs, b, "J({i}, {e});", z, th, pr, nt) for b in t_bins]
+    t_sl = [_emit(t_exprs, b, "J({i}, {e});", z, th, pr, nt, terr0, n_terr) for b in t_bins]
     tag = ROBOTS[robot]
     out = []
     out.append(f"// GENERATED by contactimplicitmpc.jl_b200/modelgen/codegen.py — do not edit.")
@@ -163,6 +186,9 @@ def generate(robot: str) -> str:
     out.append(f"constexpr int NZ = {m.nz}, NTH = {m.ntheta}, NNZ = {len(nnz)}, NNZT = {len(nnzt)}, NS = {NS};")
     out.append(f"// trig atoms: sin/cos arguments; the first NTRIG_VAR depend on z, the others only on θ")
     out.append(f"constexpr int NTRIG = {nt}, NTRIG_VAR = {ntv};")
+    out.append(f"// terrain atoms (table slots of NTRIG_VAR): contact i has (height, slope) in atom TERR0 + 2i and (cos, sin) of the")
+    out.append(f"// surface rotation in atom TERR0 + 2i + 1; NTERR = 0 on flat ground")
+    out.append(f"constexpr int NTERR = {n_terr}, TERR0 = {terr0};")
     zsub = {s_: sp.Symbol(f"z({i})") for i, s_ in enumerate(z)}
     zsub.update({s_: sp.Symbol(f"th({i})") for i, s_ in enumerate(th)})
     out.append("template <class ZA, class TA>\nCIMPC_GEN_HD double trig_arg(int k, ZA z, TA th) {")
@@ -170,9 +196,32 @@ def generate(robot: str) -> str:
     for k, a in enumerate(trig_args):
         out.append(f"    case {k}: return {pr.doprint(a.xreplace(zsub))};")
     out.append("    default: return 0.0;\n  }\n}")
-    out.append("// fills tab[2k] = sin(arg_k), tab[2k+1] = cos(arg_k) for k0 <= k < NTRIG (host-side convenience)")
+    if terr:
+        out.append(get_terrain(terr["name"]).c_source())
+        out.append("// x coordinate of contact i (the point the surface is evaluated at), from z and the trig table")
+        out.append("template <class ZA, class TA, class TR>\nCIMPC_GEN_HD double terr_x(int i, ZA z, TA th, TR tr) {")
+        out.append("  switch (i) {")
+        tsub = dict(zsub)
+        for k in range(nt):
+            tsub[sp.Symbol(f"sn{k}", real=True)] = sp.Symbol(f"tr({2 * k})")
+            tsub[sp.Symbol(f"cs{k}", real=True)] = sp.Symbol(f"tr({2 * k + 1})")
+        for i, e in enumerate(px_h):
+            out.append(f"    case {i}: return {pr.doprint(e.xreplace(tsub))};")
+        out.append("    default: return 0.0;\n  }\n}")
+    else:
+        out.append("CIMPC_GEN_HD void surf(const double, double& s, double& ds) { s = 0.0; ds = 0.0; }")
+        out.append("template <class ZA, class TA, class TR>\nCIMPC_GEN_HD double terr_x(int, ZA, TA, TR) { return 0.0; }")
+    out.append("// the two atoms of one contact from its x coordinate: (height, slope), (cos, sin) of the surface rotation")
+    out.append("// (src/simulator/environment.jl:81-96: the world→surface angle is −atan(slope))")
+    out.append("CIMPC_GEN_HD void terr_atoms(const double x, double& f, double& g, double& c, double& s) {")
+    out.append("  surf(x, f, g);\n  c = 1.0 / sqrt(1.0 + g * g);\n  s = g * c;\n}")
+    out.append("// fills tab[2k] = sin(arg_k), tab[2k+1] = cos(arg_k) for k0 <= k < NTRIG, then the terrain atoms (host-side convenience)")
     out.append("template <class ZA, class TA>\nCIMPC_GEN_HD void eval_trig(ZA z, TA th, double* tab, int k0 = 0) {")
     out.append("  for (int k = k0; k < NTRIG; ++k) { const double a = trig_arg(k, z, th); tab[2 * k] = sin(a); tab[2 * k + 1] = cos(a); }")
+    out.append("  for (int i = 0; i < NTERR; ++i) {")
+    out.append("    const double x = terr_x(i, z, th, [&](int j) { return tab[j]; });")
+    out.append("    terr_atoms(x, tab[2 * (TERR0 + 2 * i)], tab[2 * (TERR0 + 2 * i) + 1], tab[2 * (TERR0 + 2 * i + 1)], tab[2 * (TERR0 + 2 * i + 1) + 1]);")
+    out.append("  }")
     out.append("}")
     out.append("// structural non-zeros of rz (0-based row / column), column-major order")
     out.append("constexpr short RZ_ROW[NNZ] = {" + ", ".join(str(i) for i, _ in nnz) + "};")
@@ -218,6 +267,10 @@ def generate(robot: str) -> str:
     out.append("  static constexpr int NQ = gen_%s::NQ, NU = gen_%s::NU, NW = gen_%s::NW, NC = gen_%s::NC, NB = gen_%s::NB;" % ((tag,) * 5))
     out.append("  static constexpr int NZ = gen_%s::NZ, NTH = gen_%s::NTH, NNZ = gen_%s::NNZ, NNZT = gen_%s::NNZT, NS = gen_%s::NS;" % ((tag,) * 5))
     out.append("  static constexpr int NTRIG = gen_%s::NTRIG, NTRIG_VAR = gen_%s::NTRIG_VAR;" % ((tag,) * 2))
+    out.append("  static constexpr int NTERR = gen_%s::NTERR, TERR0 = gen_%s::TERR0;" % ((tag,) * 2))
+    out.append("  static constexpr CIMPC_GEN_HD bool is_terr(int k) { return NTERR > 0 && k >= TERR0 && k < TERR0 + 2 * NTERR; }")
+    out.append("  template <class ZA, class TA, class TR> static CIMPC_GEN_HD double terr_x(int i, ZA z, TA th, TR tr) { return gen_%s::terr_x(i, z, th, tr); }" % tag)
+    out.append("  static CIMPC_GEN_HD void terr_atoms(double x, double& f, double& g, double& c, double& s) { gen_%s::terr_atoms(x, f, g, c, s); }" % tag)
     out.append("  template <class ZA, class TA> static CIMPC_GEN_HD double trig_arg(int k, ZA z, TA th) { return gen_%s::trig_arg(k, z, th); }" % tag)
     out.append("  template <class ZA, class TA, class RA> static CIMPC_GEN_HD void r(ZA z, TA th, double kappa, RA out) { eval_r(z, th, kappa, out); }")
     out.append("  template <class ZA, class TA, class JA> static CIMPC_GEN_HD void rz(ZA z, TA th, JA out) { eval_rz(z, th, out); }")

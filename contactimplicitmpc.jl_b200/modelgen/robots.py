@@ -9,9 +9,11 @@ Each class restates one `src/dynamics/<robot>/model.jl` of the reference
 (dojo-sim/ContactImplicitMPC.jl @ 989c8e6): kinematics, `M_func`, `C_func` (or the
 Lagrangian it is derived from, `src/dynamics/code_gen_dynamics.jl:38-51`), `B_func`,
 `A_func`, `J_func`, `ϕ_func`, plus the per-robot contact-force / tangential-velocity
-stacks (`src/simulation/contact_methods.jl:27-48` and the per-robot overrides).  Only the
-flat environments `flat_2D_lc` / `flat_3D_lc` (`src/simulation/environments/flat.jl`) are
-restated: `surf = 0`, surface rotation = identity (`src/simulator/environment.jl:68-103`).
+stacks (`src/simulation/contact_methods.jl:27-48` and the per-robot overrides).  Environments: the flat ones
+`flat_2D_lc` / `flat_3D_lc` (`src/simulation/environments/flat.jl`: `surf = 0`, surface rotation = identity) and, for the
+planar robots, the piecewise terrains of `src/simulation/environments/piecewise.jl` (`<robot>_piecewise` models,
+`terrain.py`): the contact stacks then take the surface rotation of every contact (`src/simulator/environment.jl:68-103`)
+as the pair (cos, sin) of its angle, supplied as symbols by `symbolic.py`.
 
 All functions accept sympy symbols or plain floats (everything is built from
 `sympy.sin/cos`, +, *), so the same code yields the symbolic residual (for Jacobians
@@ -35,6 +37,7 @@ class Model:
     mu_world = 1.0
     joint_friction: list = []
     C_analytical = True  # generate_dynamics.jl: which robots derive C from the Lagrangian
+    terrain = None       # name of a non-flat 2-D environment (terrain.py), None = flat
 
     # ---- sizes (src/simulation/index.jl:371-390, environment.jl:126-127) ----
     @property
@@ -85,21 +88,28 @@ class Model:
             return [[1, -1]]
         return [[1, 0, -1, 0], [0, 1, 0, -1]]
 
-    # contact_forces on flat terrain: rotation = I  (contact_methods.jl:27-33)
-    def contact_forces(self, gamma, b):
+    # contact_forces (contact_methods.jl:27-33; per-robot forms e.g. quadruped/model.jl:472-479):
+    # λ_i = rotation(env, k_i)ᵀ [m b_i; γ_i].  `rot[i] = (c, s)`: the world→surface rotation of contact i is
+    # [[c, s], [−s, c]] with c = 1/√(1+s'²), s = s'/√(1+s'²), s' the surface slope under the contact
+    # (environment.jl:81-96: ang = −atan(s')); None = flat terrain, rotation = I.
+    def contact_forces(self, gamma, b, rot=None):
         m = self.friction_mapping()
         nf, ne = self.nf, self.world
         out = []
         for i in range(self.nc):
             bi = b[i * nf:(i + 1) * nf]
-            for row in m:
-                out.append(sum(row[j] * bi[j] for j in range(nf)))
-            out.append(gamma[i])
+            tb = [sum(row[j] * bi[j] for j in range(nf)) for row in m]
+            if rot is None:
+                out += tb + [gamma[i]]
+            else:
+                assert ne == 2, "surface rotation: planar environments only"
+                c, sn = rot[i]
+                out += [c * tb[0] - sn * gamma[i], sn * tb[0] + c * gamma[i]]
         assert len(out) == self.nc * ne
         return out
 
-    # velocity_stack on flat terrain (contact_methods.jl:42-48)
-    def velocity_stack(self, q1, q2, h):
+    # velocity_stack (contact_methods.jl:42-48; quadruped/model.jl:481-493): tangential part of rotation(env, k_i) v_i
+    def velocity_stack(self, q1, q2, h, rot=None):
         J = self.J_func(q2)
         ne = self.world
         dq = [(q2[j] - q1[j]) / h for j in range(self.nq)]
@@ -107,7 +117,11 @@ class Model:
         m = self.friction_mapping()
         out = []
         for i in range(self.nc):
-            vt = v[i * ne:i * ne + ne - 1]
+            if rot is None:
+                vt = v[i * ne:i * ne + ne - 1]
+            else:
+                c, sn = rot[i]
+                vt = [c * v[2 * i] + sn * v[2 * i + 1]]
             # transpose(friction_mapping) * v_T  ==  [v_T; -v_T]
             for j in range(self.nf):
                 out.append(sum(m[k][j] * vt[k] for k in range(ne - 1)))
@@ -411,6 +425,13 @@ class CentroidalQuadruped(Model):
 
 
 def get_model(name: str) -> Model:
+    if name.endswith("_piecewise"):
+        # get_simulation(<robot>, "piecewise1_2D_lc", "piecewise", approx = true)  (examples/*/piecewise*.jl:11-14)
+        m = get_model(name[:-len("_piecewise")])
+        assert m.world == 2, "piecewise terrains are planar"
+        m.name = name
+        m.terrain = "piecewise1_2D_lc"
+        return m
     if name == "hopper_2D":
         return Hopper2D()
     if name == "quadruped":

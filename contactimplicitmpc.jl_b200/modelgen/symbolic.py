@@ -27,6 +27,20 @@ def symbolic_C(m: Model, q, qd):
 
 def symbolic_residual(m: Model):
     """Returns (z symbols, θ symbols, κ symbol, list of nz residual expressions)."""
+    return symbolic_residual_env(m)[:4]
+
+
+def symbolic_residual_env(m: Model):
+    """Returns (z, θ, κ, r, r_diff, terr).
+
+    Flat environment: r_diff is r, terr is None.  On a terrain (`m.terrain`), contact i sees the surface through four
+    run-time values, symbols here: height `tf{i}` and slope `tg{i}` under the contact point, and (`tc{i}`, `ts{i}`) =
+    (cos, sin) of the surface rotation.  `terr["px"][i]` is the x coordinate (an expression of q2) they are evaluated
+    at.  The Jacobians are those of the reference's `approx = true` simulations (`rz_approx!`, `rθ_approx!`,
+    src/simulation/residual_approx.jl:14-99): the rotation is held constant (`dcf`, `vsq2` take the kinematics `k` as a
+    separate, undifferentiated argument) and ϕ is differentiated exactly (`rcz`, ∂ϕ_i/∂q2 = ∂p_z/∂q2 − s'(p_x) ∂p_x/∂q2).
+    `r_diff` is the residual to differentiate: it carries the surface as its tangent line `tf + tg (p_x(q2) − x0_i)`,
+    whose z-derivative is that expression whatever the expansion points `x0_i`."""
     nq, nu, nw, nc, nb, nf = m.nq, m.nu, m.nw, m.nc, m.nb, m.nf
     z = sp.symbols(f"z0:{m.nz}", real=True)
     th = sp.symbols(f"t0:{m.ntheta}", real=True)
@@ -64,19 +78,36 @@ def symbolic_residual(m: Model):
     vm2 = [(q2[i] - q1[i]) / h for i in range(nq)]
     D1L1, D2L1 = lagr(qm1, vm1)
     D1L2, D2L2 = lagr(qm2, vm2)
-    lam = m.contact_forces(g1, b1)
+    terr = None
+    rot = None
+    if m.terrain is not None:
+        assert m.world == 2
+        k = m.kinematics(q2)
+        terr = {"name": m.terrain, "px": [sp.sympify(k[2 * i]) for i in range(nc)],
+                "tf": sp.symbols(f"tf0:{nc}", real=True), "tg": sp.symbols(f"tg0:{nc}", real=True),
+                "tc": sp.symbols(f"tc0:{nc}", real=True), "ts": sp.symbols(f"ts0:{nc}", real=True),
+                "x0": sp.symbols(f"tx0:{nc}", real=True)}
+        rot = list(zip(terr["tc"], terr["ts"]))
+    lam = m.contact_forces(g1, b1, rot)
     Lam = _matvec_T(m.J_func(q2), lam, nq)
     Bu = _matvec_T(m.B_func(qm2), u1, nq)
     Aw = _matvec_T(m.A_func(qm2), w1, nq)
     r = [0.5 * h * D1L1[i] + D2L1[i] + 0.5 * h * D1L2[i] - D2L2[i] + Bu[i] + Aw[i] + Lam[i]
          - h * m.joint_friction[i] * vm2[i] for i in range(nq)]
-    phi = m.phi_func(q2)
-    vT = m.velocity_stack(q1, q2, h)
-    r += [s1[i] - phi[i] for i in range(nc)]
+    phi = m.phi_func(q2)  # height of the contact points over z = 0
+    vT = m.velocity_stack(q1, q2, h, rot)
+    n_dyn = len(r)
+    r += [s1[i] - phi[i] + (terr["tf"][i] if terr else 0) for i in range(nc)]
     r += [eta1[i] - vT[i] - psi1[i // nf] for i in range(nb)]
     r += [s2[i] - (mu * g1[i] - sum(b1[i * nf:(i + 1) * nf])) for i in range(nc)]
     r += [g1[i] * s1[i] - kappa for i in range(nc)]
     r += [b1[i] * eta1[i] - kappa for i in range(nb)]
     r += [psi1[i] * s2[i] - kappa for i in range(nc)]
     assert len(r) == m.nz
-    return z, th, kappa, [sp.sympify(e) for e in r]
+    r = [sp.sympify(e) for e in r]
+    r_diff = r
+    if terr:
+        r_diff = list(r)
+        for i in range(nc):
+            r_diff[n_dyn + i] = r[n_dyn + i] + terr["tg"][i] * (terr["px"][i] - terr["x0"][i])
+    return z, th, kappa, r, r_diff, terr

@@ -257,9 +257,11 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n_rollouts, const double* q0, c
                          const double* w, const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts,
                          double* q2, double* gamma, double* b, uint8_t* status, int32_t* iters, void* stream);
 
-/* Same step with one more output: phi nc × n DEVICE or NULL — the signed distances ϕ(q_{t+2}) of the solution (the
- * slack s1 of the converged point), what `update_altitude!` reads at the step of largest impact
- * (src/controller/mpc_utils.jl:109-135: `s.ϕ(ϕ, traj.q[idx_max+2])`). */
+/* Same step with one more output: phi nc × n DEVICE or NULL — ϕ(q_{t+2}) of the solution evaluated with the POLICY's
+ * flat-ground model, i.e. the heights of the contact points: what `update_altitude!` reads at the step of largest impact
+ * (src/controller/mpc_utils.jl:109-135: `s.ϕ(ϕ, traj.q[idx_max+2])` with `s` the simulation the policy was built on).
+ * On a flat-ground context this is the slack s1 of the converged point; on a `*_piecewise` context it is s1 plus the
+ * surface height under the contact. */
 int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n_rollouts, const double* q0, const double* q1, const double* u,
                             const double* w, const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts,
                             double* q2, double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters,

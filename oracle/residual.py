@@ -75,7 +75,12 @@ def symbolic_C(m: Model, q, qd):
     return C
 
 
-def symbolic_residual(m: Model):
+def symbolic_residual(m: Model, surface=None):
+    """`surface`: None on flat ground, else three lists of nc symbols (f, c, s): height of the surface under every
+    contact point and (cos, sin) of its world→surface rotation [[c, s], [−s, c]] (planar environments,
+    src/simulator/environment.jl:81-96).  They enter as in the per-robot contact stacks of the reference
+    (e.g. src/dynamics/quadruped/model.jl:472-493, hopper_2D/model.jl:74-86): λ_i = Rᵀ[m b_i; γ_i], tangential
+    velocity = (R v_i)[1], ϕ_i = p_z − surf(p_x) (flamingo/model.jl:391-401)."""
     nq = m.nq
     idx = Index(m)
     z = sp.symbols(f"z0:{idx.nz}", real=True)
@@ -116,6 +121,11 @@ def symbolic_residual(m: Model):
     D1L1, D2L1 = lagr_derivs(qm1, vm1)
     D1L2, D2L2 = lagr_derivs(qm2, vm2)
     lam = m.contact_forces(g1, b1)
+    if surface is not None:
+        assert m.world == 2
+        _, cs, sn = surface
+        lam = [w for i in range(m.nc) for w in (cs[i] * lam[2 * i] - sn[i] * lam[2 * i + 1],
+                                                 sn[i] * lam[2 * i] + cs[i] * lam[2 * i + 1])]
     Lam = _matvec_T(m.J_func(q2), lam, nq)
     Bu = _matvec_T(m.B_func(qm2), u1, nq)
     Aw = _matvec_T(m.A_func(qm2), w1, nq)
@@ -126,6 +136,13 @@ def symbolic_residual(m: Model):
     phi = m.phi_func(q2)
     vT = m.velocity_stack(q1, q2, h)
     nc, nf = m.nc, m.nf
+    if surface is not None:
+        f, cs, sn = surface
+        phi = [phi[i] - f[i] for i in range(nc)]
+        Jc = m.J_func(q2)
+        v = [sum(Jc[a][j] * (q2[j] - q1[j]) / h for j in range(nq)) for a in range(2 * nc)]
+        vt = [cs[i] * v[2 * i] + sn[i] * v[2 * i + 1] for i in range(nc)]
+        vT = [w for i in range(nc) for w in (vt[i], -vt[i])]
     r = list(d)
     r += [s1[i] - phi[i] for i in range(nc)]
     r += [eta1[i] - vT[i] - psi1[i // nf] for i in range(m.nb)]          # η1 − vT − Eᵀψ1
@@ -163,6 +180,64 @@ class Residual:
         return np.asarray(self._rth(z, th), dtype=np.float64)
 
 
+class TerrainResidual:
+    """r, rz, rθ of a planar robot on a piecewise terrain, as the reference's `approx = true` simulations define them
+    (`get_simulation(robot, "piecewise1_2D_lc", "piecewise", approx = true)`; src/simulation/residual_approx.jl:14-99):
+    the Jacobians hold the surface ROTATION under every contact fixed (`dcf`, `vsq2`, `vsq1h` take the kinematics `k` as
+    an undifferentiated argument) and differentiate everything else, ϕ included (`rcz`, `rcθ`).
+
+    The Jacobians here are complex-step derivatives of the residual with the rotation frozen at the evaluation point
+    and the surface height continued along its tangent (oracle/terrain.py) — exact to round-off, and a different route
+    from the product's symbolic one (modelgen/symbolic.py), so the two check each other."""
+
+    def __init__(self, name: str, terrain: str = "piecewise1_2D_lc"):
+        from .terrain import get_terrain
+        assert name.endswith("_piecewise")
+        self.model = get_model(name[:-len("_piecewise")])
+        self.idx = Index(self.model)
+        self.terrain = get_terrain(terrain)
+        nc = self.model.nc
+        surface = (sp.symbols(f"sf0:{nc}", real=True), sp.symbols(f"sc0:{nc}", real=True), sp.symbols(f"ss0:{nc}", real=True))
+        z, th, kappa, r = symbolic_residual(self.model, surface)
+        flat = [w for grp in surface for w in grp]
+        self._r = sp.lambdify([z, th, kappa, flat], sp.Matrix(r), modules="numpy", cse=True)
+        q2 = [z[i] for i in self.idx.q2]
+        kin = self.model.kinematics(q2)
+        self._px = sp.lambdify([q2], [kin[2 * i] for i in range(nc)], modules="numpy")
+
+    def _surface(self, z, rot_at=None):
+        """[f; c; s] at z; the rotation is evaluated at `rot_at` (default: z itself)."""
+        px = np.asarray(self._px(np.asarray(z)[self.idx.q2]))
+        pr = px if rot_at is None else np.asarray(self._px(np.asarray(rot_at)[self.idx.q2]))
+        f = [self.terrain.height(x) for x in px]
+        cs = [self.terrain.rotation(x) for x in pr]
+        return np.array(f + [c for c, _ in cs] + [s_ for _, s_ in cs])
+
+    def r(self, z, th, kappa):
+        return np.asarray(self._r(z, th, kappa, self._surface(z)), dtype=np.float64).reshape(-1)
+
+    def _complex_step(self, z, th, wrt_z: bool):
+        z = np.asarray(z, dtype=np.float64)
+        th = np.asarray(th, dtype=np.float64)
+        n = z.size if wrt_z else th.size
+        J = np.zeros((z.size, n))
+        eps = 1e-30
+        for j in range(n):
+            zc, tc = z.astype(np.complex128), th.astype(np.complex128)
+            (zc if wrt_z else tc)[j] += 1j * eps
+            rc = np.asarray(self._r(zc, tc, 0.0, self._surface(zc, rot_at=z)), dtype=np.complex128).reshape(-1)
+            J[:, j] = rc.imag / eps
+        return J
+
+    def rz(self, z, th):
+        return self._complex_step(z, th, True)
+
+    def rth(self, z, th):
+        return self._complex_step(z, th, False)
+
+
 @functools.lru_cache(maxsize=None)
-def get_residual(name: str) -> Residual:
+def get_residual(name: str):
+    if name.endswith("_piecewise"):
+        return TerrainResidual(name)
     return Residual(name)

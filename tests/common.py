@@ -131,6 +131,7 @@ def independent_violation(robot, lin, knot, theta, z, alt=None):
 # ---- the PRODUCT's generated residual code evaluated on the host (no oracle involved) ---------------------------
 GEN_DIR = os.path.join(ROOT, "contactimplicitmpc.jl_b200", "csrc", "gen")
 GEN_TAG = {"hopper_2D": "hopper2d", "quadruped": "quadruped", "flamingo": "flamingo", "centroidal_quadruped": "centroidal",
+           "hopper_2D_piecewise": "hopper2d_piecewise", "flamingo_piecewise": "flamingo_piecewise", "quadruped_piecewise": "quadruped_piecewise",
            "quadruped_payload": "quadruped_payload", "centroidal_quadruped_payload": "centroidal_payload"}
 _GEN_SHIM = r'''
 #include "residual_%(tag)s.h"
@@ -160,7 +161,7 @@ class GeneratedResidual:
         import ctypes as C
         import subprocess
         tag = GEN_TAG[robot]
-        nq, nu, nw, nc, nb = SIZES[robot.replace("_payload", "")]
+        nq, nu, nw, nc, nb = SIZES[robot.replace("_payload", "").replace("_piecewise", "")]
         self.nz, self.nth = nq + 4 * nc + 2 * nb, 2 * nq + nu + nw + 2
         src = os.path.join(workdir, f"shim_{tag}.cpp")
         so = os.path.join(workdir, f"shim_{tag}.so")

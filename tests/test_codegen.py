@@ -78,3 +78,46 @@ def test_generated_residual_matches_oracle(tmp_path, robot, tag):
         dense_t = np.zeros((nz, nth)); dense_t[trow, tcol] = Jt
         assert np.abs(dense_t - To).max() <= 1e-9 * max(1.0, np.abs(To).max())
         assert set(zip(*np.nonzero(To))) <= set(zip(trow, tcol))
+
+
+@pytest.mark.parametrize("robot,tag", [("hopper_2D_piecewise", "hopper2d_piecewise"), ("flamingo_piecewise", "flamingo_piecewise"),
+                                       ("quadruped_piecewise", "quadruped_piecewise")])
+def test_generated_terrain_residual_matches_oracle(tmp_path, robot, tag):
+    """Planar robots on `piecewise1_2D_lc` (get_simulation(robot, "piecewise1_2D_lc", "piecewise", approx = true)): the
+    generated r and the `approx` Jacobians (surface rotation held fixed, src/simulation/residual_approx.jl:14-99) against
+    the oracle, whose Jacobians are complex-step derivatives — on the flat part, both ramps and inside both smoothed kinks."""
+    from oracle.residual import get_residual
+    src = tmp_path / "shim.cpp"
+    src.write_text(SHIM % {"tag": tag})
+    so = tmp_path / "shim.so"
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", f"-I{GEN}", str(src), "-o", str(so)], check=True)
+    lib = C.CDLL(str(so))
+    lib.r_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    res = get_residual(robot)
+    nz, nth = res.idx.nz, res.idx.ntheta
+    nnz, nnzt = lib.nnz(), lib.nnzt()
+    row = np.zeros(nnz, np.int32); col = np.zeros(nnz, np.int32)
+    lib.pattern(row.ctypes.data_as(C.c_void_p), col.ctypes.data_as(C.c_void_p))
+    trow = np.zeros(nnzt, np.int32); tcol = np.zeros(nnzt, np.int32)
+    lib.pattern_t(trow.ctypes.data_as(C.c_void_p), tcol.ctypes.data_as(C.c_void_p))
+    rng = np.random.default_rng(1)
+    sections = set()
+    for x_body in (-1.0, 0.2, 0.35, 0.45, 0.5, 0.55, 0.65, 1.0, 1.6, 1.85, 1.95, 2.0, 2.05, 2.15, 2.6, 4.0):
+        z = rng.random(nz) + 0.1
+        z[res.idx.q2[2:]] = 0.6 * rng.standard_normal(res.model.nq - 2)
+        z[0] = x_body
+        th = rng.random(nth) * 0.5 + 0.1
+        th[-1] = 0.01 + 0.01 * rng.random()
+        for x in res._px(z[res.idx.q2]):
+            sections.add(int(np.searchsorted([0.4, 0.6, 1.9, 2.1], x)))
+        r = np.zeros(nz); J = np.zeros(nnz); Jt = np.zeros(nnzt)
+        lib.r_eval(z.ctypes.data, th.ctypes.data, 1e-4, r.ctypes.data)
+        lib.rz_eval(z.ctypes.data, th.ctypes.data, J.ctypes.data)
+        lib.rth_eval(z.ctypes.data, th.ctypes.data, Jt.ctypes.data)
+        ro, Jo, To = res.r(z, th, 1e-4), res.rz(z, th), res.rth(z, th)
+        assert np.abs(r - ro).max() <= 1e-10 * max(1.0, np.abs(ro).max())
+        dense = np.zeros((nz, nz)); dense[row, col] = J
+        assert np.abs(dense - Jo).max() <= 1e-9 * max(1.0, np.abs(Jo).max())
+        dense_t = np.zeros((nz, nth)); dense_t[trow, tcol] = Jt
+        assert np.abs(dense_t - To).max() <= 1e-9 * max(1.0, np.abs(To).max())
+    assert sections == {0, 1, 2, 3, 4}, sections  # every piece of the terrain was under some contact

@@ -56,3 +56,37 @@ def test_solves_after_device_linearization_match_uploaded(cuda_device, robot, mo
     im_dev.linearize(lin["z0"], lin["th0"], float(lin["kappa"]))
     zd, _, sd, idd = im_dev.solve_host(knot, theta, q2)
     assert np.array_equal(zd, zb) and np.array_equal(idd, ib)
+
+
+@pytest.mark.parametrize("robot", ["hopper_2D", "flamingo", "quadruped"])
+def test_device_linearization_on_piecewise_terrain_matches_oracle(cuda_device, robot):
+    """`cimpc_linearize` on a `<robot>_piecewise` context (LinearizedStep of an `approx = true` simulation,
+    src/simulation/residual_approx.jl:14-99) against the oracle's terrain residual: r, rz, rθ at reference knots moved
+    over the terrain."""
+    import cimpc_b200 as cb
+    from oracle.residual import get_residual
+    lin = load_lin(robot)
+    res = get_residual(robot + "_piecewise")
+    nq = SIZES[robot][0]
+    H = lin["z0"].shape[0]
+    z0, th0 = lin["z0"].copy(), lin["th0"].copy()
+    x_new = np.linspace(0.1, 2.6, H)
+    lift = np.array([res.terrain.height(x) for x in x_new])
+    dx = x_new - z0[:, 0]
+    for a in (z0[:, 0:nq], th0[:, 0:nq], th0[:, nq:2 * nq]):  # q2, q0, q1 move together
+        a[:, 0] += dx
+        a[:, 1] += lift
+    kappa = float(lin["kappa"])
+    im = cb.ImplicitTrajectory(*SIZES[robot], z0, th0, kappa=kappa, mode="configuration", model=robot + "_piecewise")
+    r0, rz0, rth0 = im.get_linearization()
+    worst = 0.0
+    for t in range(0, H, max(1, H // 12)):
+        for name, a, b in (("r0", r0[t], res.r(z0[t], th0[t], kappa)), ("rz0", rz0[t], res.rz(z0[t], th0[t])),
+                           ("rth0", rth0[t], res.rth(z0[t], th0[t]))):
+            err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
+            worst = max(worst, err)
+            assert err < 1e-9, (robot, t, name, err)
+    # and it differs from the flat linearization where the ground is not flat
+    im_flat = cb.ImplicitTrajectory(*SIZES[robot], z0, th0, kappa=kappa, mode="configuration")
+    rf, rzf, _ = im_flat.get_linearization()
+    assert np.abs(rf - r0).max() > 1e-3 and np.abs(rzf - rz0).max() > 1e-2

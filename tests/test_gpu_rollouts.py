@@ -338,3 +338,58 @@ def test_drop_box_simulator_failures_match_oracle(cuda_device):
           f"both {np.sum(fd & fc)}, same step {np.sum((fail_dev == fail_cpu) & fd)}")
     assert np.sum(fd ^ fc) <= max(2, R // 16), (fail_dev, fail_cpu)
     assert abs(fd.mean() - fc.mean()) <= 0.05
+
+
+def test_flamingo_climbs_the_piecewise_terrain_on_device(cuda_device):
+    """examples/flamingo/piecewise.jl with the simulator ON the terrain (`simulator(s_sim, …)`, s_sim =
+    get_simulation("flamingo", "piecewise1_2D_lc", "piecewise", approx = true)): the policy is linearized on flat ground
+    (:12, :37) and learns the ground height under every contact from `update_altitude!` (`altitude_update = true`,
+    `altitude_impact_threshold = 0.02`, :43-47).  The plant is the `flamingo_piecewise` model of this library.  The nominal
+    rollout must walk up the 10° ramp (from x = 0.5) for 2500 steps with its feet on the surface; without the altitude
+    update the same policy does not get up the ramp."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait
+    from oracle.residual import get_residual
+    from oracle.trajectory import trajectory_from_gait
+    robot, H_mpc, N, kappa, H_sim, R = "flamingo", 15, 5, 1.0e-4, 2500, 4
+    res, tres = get_residual(robot), get_residual("flamingo_piecewise")
+    m = res.model
+    gait = load_gait(robot)
+    ref = trajectory_from_gait(m, gait)
+    h = gait["h"]
+    ipo = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=kappa, undercut=5.0, diff_sol=True)
+    oq = np.tile(1e-1 * np.array([3e2, 1e-6, 3e2, 1, 1, 1, 1, 0.1, 0.1]), (H_mpc, 1))
+    ou = np.tile(3e-1 * np.array([0.1, 0.1, 0.3, 0.3, 2, 2]), (H_mpc, 1))
+    ov = np.tile(1e-3 * np.array([1e0, 1, 1e4, 1, 1, 1, 1, 1e4, 1e4]), (H_mpc, 1))
+    sim_opts = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=1e-8, max_ls=25, eps_min=0.05, undercut=float("inf"), gamma_reg=0.0)
+
+    def loop(altitude_update, steps):
+        im = cb.ImplicitTrajectory(*SIZES[robot], ref.z, ref.theta, kappa=kappa, mode="configurationforce", opts=ipo)
+        mc = cb.MonteCarloRollouts(im, ref.q, ref.u, ref.theta[0, -2], m.mu_world, h, H_mpc=H_mpc, N_sample=N, obj_q=oq,
+                                   obj_u=ou, kappa=kappa, n_rollouts=R, newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5),
+                                   sim_opts=sim_opts, obj_gamma=np.full((H_mpc, m.nc), 1e-100),
+                                   obj_b=np.full((H_mpc, m.nb), 1e-100), obj_v=ov, ref_gamma=ref.gamma, ref_b=ref.b,
+                                   altitude_update=altitude_update, altitude_impact_threshold=0.02, sim_model="flamingo_piecewise")
+        q1 = np.tile(ref.q[1], (R, 1))
+        v1 = np.tile((ref.q[1] - ref.q[0]) / h, (R, 1))
+        v1[1:] *= 1.0 + 0.02 * np.random.default_rng(61).standard_normal((R - 1, 1))
+        out = mc.run(torch.from_numpy(q1).to(cuda_device), torch.from_numpy(v1).to(cuda_device), steps)
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items() if v is not None}
+
+    a = loop(True, H_sim)
+    assert a["status"][0], "the nominal rollout must complete"
+    assert a["status"].sum() >= R - 1
+    q = a["q"][:, 0]
+    assert q[-1, 0] > 1.5                                        # it is well up the ramp (which starts at x = 0.5) …
+    lift = tres.terrain.height(q[-1, 0])
+    assert lift > 0.15 and abs((q[-1, 1] - q[1, 1]) - lift) < 0.03  # … and the body rose with the ground
+    gaps = np.array([[res.model.phi_func(list(qt))[c] - tres.terrain.height(x) for c, x in enumerate(tres._px(qt))]
+                     for qt in q[1::25]], dtype=float)
+    assert gaps.min() > -2e-3                                    # no contact point below the surface
+    assert (gaps.min(axis=1) < 2e-3).mean() > 0.9                # and some foot is on it
+    # the measured altitudes are the surface heights under the feet at their last impacts
+    assert np.all(a["alt"][0] > 0.1) and np.all(a["alt"][0] < lift + 0.06)
+    b = loop(False, H_sim)
+    assert (not b["status"][0]) or b["q"][-1, 0, 0] < q[-1, 0] - 0.3, "altitude_update = false should not get up the ramp"

@@ -64,3 +64,65 @@ def test_sim_step_matches_oracle(cuda_device, robot, tag):
             assert same >= int(0.97 * st.sum()) and worst <= tol, (same, worst)
         else:
             assert same >= int(0.9 * st.sum())
+
+
+@pytest.mark.parametrize("robot", ["hopper_2D", "flamingo", "quadruped"])
+def test_sim_step_on_piecewise_terrain_matches_oracle(cuda_device, robot):
+    """The planar robots on `piecewise1_2D_lc` (examples/*/piecewise*.jl:11-14: get_simulation(robot, "piecewise1_2D_lc",
+    "piecewise", approx = true)): gait states moved along x over the flat part, both ramps and both smoothed kinks and
+    lifted by the terrain height; the device step (generated residual with terrain atoms, `approx` Jacobians) against the
+    oracle's nonlinear IP (complex-step Jacobians with the surface rotation held fixed)."""
+    import torch
+    import cimpc_b200 as cb
+    from oracle.ip import IPOptions
+    from oracle.residual import get_residual
+    from oracle.simulator import nonlinear_ip_solve
+    tag = robot + "_piecewise"
+    res = get_residual(tag)
+    m = res.model
+    gait = load_gait(robot)
+    H = gait["u"].shape[0]
+    h_sim = gait["h"] / 5
+    rng = np.random.default_rng(51)
+    R = 40
+    t = rng.integers(0, H, R)
+    q1 = gait["q"][t + 1] + 0.002 * rng.standard_normal((R, m.nq))
+    v = (gait["q"][t + 1] - gait["q"][t]) / gait["h"]
+    x_new = rng.uniform(-0.2, 2.8, R)
+    x_new[:6] = [0.45, 0.5, 0.55, 1.95, 2.0, 2.05]  # bodies over the kinks
+    q1[:, 0] = x_new
+    q1[:, 1] += np.array([res.terrain.height(x) for x in x_new])
+    q0 = q1 - h_sim * v * (1 + 0.05 * rng.standard_normal((R, 1)))
+    u = gait["u"][t] / 5 * (1 + 0.1 * rng.standard_normal((R, m.nu)))
+    mu = m.mu_world
+    o = cb.InteriorPointOptions(r_tol=1e-8, kappa_tol=1e-8, max_ls=0, eps_min=0.25, undercut=float("inf"), gamma_reg=0.1)
+    sim = cb.Simulator(*SIZES[robot], opts=o, model=tag)
+    dev = cuda_device
+    q2, gam, b, st, it = sim.step(torch.from_numpy(q0).to(dev), torch.from_numpy(q1).to(dev), torch.from_numpy(u).to(dev), mu, h_sim)
+    torch.cuda.synchronize()
+    q2, gam, b, st, it = q2.cpu().numpy(), gam.cpu().numpy(), b.cpu().numpy(), st.cpu().numpy().astype(bool), it.cpu().numpy()
+    oo = IPOptions(r_tol=1e-8, kappa_tol=1e-8, max_ls=0, eps_min=0.25, undercut=np.inf, gamma_reg=0.1)
+    i = res.idx
+    same, worst, status_mismatch, sloped = 0, 0.0, 0, 0
+    for r in range(R):
+        z = np.ones(i.nz); z[i.q2] = q1[r]
+        th = np.concatenate([q0[r], q1[r], u[r], np.zeros(m.nw), [mu], [h_sim]])
+        ok, zo, ito = nonlinear_ip_solve(res, z, th, oo)
+        status_mismatch += int(ok != st[r])
+        if ok and st[r] and ito == it[r]:
+            same += 1
+            sc = max(1.0, np.abs(zo[i.g1]).max(), np.abs(zo[i.b1]).max())
+            # the net friction force m·b = b₊ − b₋ of every contact is what the dynamics see; the split between the two
+            # directions is ill-conditioned at a contact about to slide (one rollout of 40 here: 2e-3 on b with q2 equal to
+            # 1e-10 and γ to 6e-9; quadruped: 1.4e-2 relative), so it is held to a looser bound
+            net = lambda bb: bb[0::2] - bb[1::2]  # noqa: E731
+            worst = max(worst, np.abs(q2[r] - zo[i.q2]).max(), np.abs(gam[r] - zo[i.g1]).max() / sc,
+                        np.abs(net(b[r]) - net(zo[i.b1])).max() / sc)
+            assert np.abs(b[r] - zo[i.b1]).max() <= 5e-2 * sc
+            # the solution satisfies the terrain's own residual (independent of the iteration path)
+            zd = zo.copy(); zd[i.q2] = q2[r]; zd[i.g1] = gam[r]; zd[i.b1] = b[r]
+            assert np.abs(res.r(zd, th, 0.0)[i.dyn]).max() < 1e-6
+            sloped += int(any(abs(res.terrain.slope(x)) > 0 for x in res._px(q2[r])))
+    assert st.mean() > 0.9 and status_mismatch <= 1, (st.mean(), status_mismatch)
+    assert same >= int(0.95 * st.sum()) and worst <= 5e-7, (same, worst)
+    assert sloped >= R // 3  # the comparison did exercise the ramps

@@ -234,3 +234,37 @@ def test_hopper_single_policy_call():
     window = update_window(window, H_ref)
     assert window[0] == 1 and np.allclose(ptraj.q[0], ref.q[1])
     assert np.allclose(ptraj.q[H_ref + 1] - ptraj.q[1], get_stride(m, ref))
+
+
+def test_piecewise_terrain_and_its_approx_jacobian():
+    """`piecewise1_2D_lc` (src/simulation/environments/piecewise.jl:40-125): the surface is C¹ across the smoothed kinks
+    (the reference asserts the cubic fits at :57-58, :77-78), the rotation of environment.jl:81-96 is the pair
+    (1, s')/√(1+s'²), and on the straight pieces — where the rotation does not change — the `approx` Jacobian of
+    residual_approx.jl:14-99 IS the Jacobian of the residual (central differences)."""
+    from oracle.residual import get_residual
+    from oracle.terrain import get_terrain
+    ter = get_terrain("piecewise1_2D_lc")
+    m_ss = np.tan(np.deg2rad(10.0))
+    assert ter.height(0.2) == 0.0 and abs(ter.height(1.0) - 0.5 * m_ss) < 1e-15 and abs(ter.height(3.0) - 1.25 * m_ss) < 1e-15
+    for x in (0.4, 0.6, 1.9, 2.1):
+        assert abs(ter.height(x - 1e-9) - ter.height(x + 1e-9)) < 1e-8 and abs(ter.slope(x - 1e-9) - ter.slope(x + 1e-9)) < 1e-7
+    for x in (0.1, 0.5, 1.0, 2.0, 3.0):
+        c, s = ter.rotation(x)
+        g = ter.slope(x)
+        assert abs(c - 1 / np.hypot(1, g)) < 1e-15 and abs(s - g / np.hypot(1, g)) < 1e-15
+    res = get_residual("hopper_2D_piecewise")
+    m = res.model
+    rng = np.random.default_rng(0)
+    z = np.abs(rng.standard_normal(m.nz)) + 0.1
+    th = rng.standard_normal(m.ntheta); th[-1] = 0.01; th[-2] = 0.8
+    for foot_x, straight in ((0.2, True), (1.0, True), (3.0, True), (0.5, False)):
+        z[0] = foot_x - z[3] * np.sin(z[2])
+        J = res.rz(z, th)
+        Jf = np.zeros_like(J)
+        for j in range(m.nz):
+            e = np.zeros(m.nz); e[j] = 1e-6
+            Jf[:, j] = (res.r(z + e, th, 0.0) - res.r(z - e, th, 0.0)) / 2e-6
+        if straight:
+            assert np.abs(J - Jf).max() < 1e-6
+        else:  # inside a kink the neglected curvature terms are there
+            assert np.abs(J - Jf).max() > 1e-2
