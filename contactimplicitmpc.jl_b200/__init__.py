@@ -7,6 +7,6 @@ from .solver import (ImplicitTrajectory, InteriorPointOptions, Newton, NewtonOpt
 from .sharding import (gather_rollout_results, gather_rollouts_capi, init_comm, shard_rollouts,  # noqa: F401,E402
                        sum_statistics)
 from .rollout import GroupedRollouts, MonteCarloRollouts, ReferenceWindow, quadruped_initial_configurations  # noqa: F401,E402
-from .trajectory import ContactTraj, JLD2File, load_gait, load_traj, repeat_ref_traj, save_traj, tracking_error  # noqa: F401,E402
+from .trajectory import ContactTraj, JLD2File, load_gait, load_traj, repeat_ref_traj, save_gait, save_traj, tracking_error  # noqa: F401,E402
 from .disturbances import (Disturbances, EmptyDisturbances, ImpulseDisturbance, OpenLoopDisturbance,  # noqa: F401,E402
                            RandomDisturbance)

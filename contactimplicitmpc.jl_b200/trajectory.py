@@ -8,7 +8,9 @@
                                 `update_z!`, `update_θ!`, `pack_z` (src/simulation/index.jl:437-441)
   * `repeat_ref_traj`, `tracking_error`   trajectory.jl:84-113, 188-217 — the closed-loop metrics the reference's
                                 end-to-end tests pin (test/controller/mpc_quadruped.jl:59-64)
-  * `save_traj` / `load_traj`   npz round trip (the reference uses JLD2 `@save`, src/dynamics/utils.jl:129-152)
+  * `save_traj` / `load_traj`   npz round trip of a whole `ContactTraj`
+  * `save_gait`                 writes a `:split_traj_alt` JLD2 gait file (`jld2_writer.py`: byte-for-byte what JLD2.jl
+                                wrote for the reference's own gaits; the reference uses `@save`, src/dynamics/utils.jl:129-152)
 
 A Julia caller keeps using JLD2.jl; this reader exists so that the Python mirror consumes the SAME files.
 Supported HDF5 subset (what JLD2 0.1.1 wrote for these files): v2 superblock at a 512-byte base offset, v2 object
@@ -327,6 +329,16 @@ class ContactTraj:
 def save_traj(path: str, tr: ContactTraj):
     np.savez_compressed(path, q=tr.q, u=tr.u, w=tr.w, gamma=tr.gamma, b=tr.b, z=tr.z, theta=tr.theta, h=tr.h,
                         kappa=tr.kappa, sizes=np.array([tr.nq, tr.nu, tr.nw, tr.nc, tr.nb]))
+
+
+def save_gait(path: str, tr: ContactTraj, mu: float | None = None, julia: str = "1.6.0"):
+    """`@save path qm um γm bm ψm ηm μm hm` of a trajectory: the file `get_trajectory(...; load_type = :split_traj_alt)`
+    reads.  ψ and η are taken from z (index.jl: z = [q2; γ1; b1; ψ1; s1; η1; s2]); μ defaults to the one stored in θ."""
+    from .jld2_writer import save_split_traj_alt
+    nq, nc, nb = tr.nq, tr.nc, tr.nb
+    psi = tr.z[:, nq + nc + nb:nq + 2 * nc + nb]
+    eta = tr.z[:, nq + 3 * nc + nb:nq + 3 * nc + 2 * nb]
+    save_split_traj_alt(path, tr.q, tr.u, tr.gamma, tr.b, psi, eta, float(tr.theta[0, -2]) if mu is None else mu, tr.h, julia)
 
 
 def load_traj(path: str) -> ContactTraj:
