@@ -246,7 +246,10 @@ end
 # ---------------------------------------------------------------------------------------------------------------
 
 """`get_simulation(name, …; model_variable_name = "quadruped_payload")`: a context whose generated residual is the named
-model's (examples/quadruped/payload.jl:10-14) — used for the simulated plant and for device-side linearization."""
+model's (examples/quadruped/payload.jl:10-14) — used for the simulated plant and for device-side linearization.
+`get_simulation(robot, "piecewise1_2D_lc", "piecewise", approx = true)` (examples/flamingo/piecewise.jl:11) is
+`model_name = "flamingo_piecewise"` (also `"hopper_2D_piecewise"`, `"quadruped_piecewise"`): the plant on the piecewise
+terrain; `sim_step!` on such a context returns ϕ in the flat frame of the policy, which is what `update_altitude!` wants."""
 function create_named(desc::ModelDesc, model_name::String; device = 0)
     ctx = Ref{Ptr{Cvoid}}()
     check(C_NULL, ccall((:cimpc_create_named, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint, Ref{ModelDesc}, Cstring),
