@@ -6,6 +6,9 @@
 #include <mutex>
 
 #include "ip_kernel.cuh"
+#ifdef CIMPC_WITH_IP_V3
+#include "ip_kernel2.cuh"  // measured-and-rejected two-rows-per-lane variant (profiles/r02_ip_two_rows_per_lane.md)
+#endif
 #include "lin_kernel.cuh"
 #include "newton_kernel.cuh"
 #include "newton_cta.cuh"
@@ -186,30 +189,93 @@ LinLayout layout_of() {
   return l;
 }
 
+// ---- kernel v3 (ip_kernel2.cuh): two rows per lane, for the instances with G >= 16 ------------------------------
+// Measured slower than v2 (0.80-0.90x, profiles/r02_ip_two_rows_per_lane.md), so it is compiled only with
+// -DCIMPC_WITH_IP_V3 (CIMPC_EXTRA_NVCC_FLAGS); then CIMPC_IP_KERNEL=v2 / v3 selects the kernel per launch
+// (scripts/gpu_ip_ab.py).
+#ifndef CIMPC_IP2_THREADS_16
+#define CIMPC_IP2_THREADS_16 384  // G = 16 (quadruped, flamingo): 8 lanes per subproblem, 48 subproblems per CTA
+#endif
+#ifndef CIMPC_IP2_MINCTAS_16
+#define CIMPC_IP2_MINCTAS_16 1
+#endif
+#ifndef CIMPC_IP2_THREADS_32
+#define CIMPC_IP2_THREADS_32 256  // G = 32 (centroidal): 16 lanes per subproblem, 16 subproblems per CTA
+#endif
+#ifndef CIMPC_IP_DEFAULT_VERSION
+#define CIMPC_IP_DEFAULT_VERSION 2
+#endif
+template <class D>
+constexpr bool ip2_supported() {
+#ifdef CIMPC_WITH_IP_V3
+  return D::G >= 16 && D::NRP == D::NR;
+#else
+  return false;
+#endif
+}
+template <class D>
+constexpr int ip2_threads() { return D::G == 32 ? CIMPC_IP2_THREADS_32 : CIMPC_IP2_THREADS_16; }
+template <class D>
+constexpr int ip2_minctas() { return D::G == 32 ? 1 : CIMPC_IP2_MINCTAS_16; }
+inline int ip_kernel_version() {  // read per launch (a launch costs more than a getenv): tests switch it inside one process
+  const char* e = getenv("CIMPC_IP_KERNEL");
+  if (e && e[0] == 'v' && (e[1] == '2' || e[1] == '3')) return e[1] - '0';
+  return CIMPC_IP_DEFAULT_VERSION;
+}
+
 template <class D>
 cudaError_t prepare_ip() {  // opt in to > 48 KB of dynamic shared memory (once per instance and device)
   static SmemOptIn opt;
-  return opt.ensure(ip_solve_kernel<D, ip_threads<D>()>, KernelSmem<D, ip_threads<D>()>::BYTES);
+  cudaError_t e = opt.ensure(ip_solve_kernel<D, ip_threads<D>()>, KernelSmem<D, ip_threads<D>()>::BYTES);
+#ifdef CIMPC_WITH_IP_V3
+  if constexpr (ip2_supported<D>()) {
+    static SmemOptIn opt2;
+    if (e == cudaSuccess)
+      e = opt2.ensure(ip_solve2_kernel<D, ip2_threads<D>(), ip2_minctas<D>()>, KernelSmem2<D, ip2_threads<D>()>::BYTES);
+  }
+#endif
+  return e;
 }
 
 template <class D>
 cudaError_t occupancy_ip(int* blocks_per_sm) {
   cudaError_t e = prepare_ip<D>();
   if (e != cudaSuccess) return e;
+#ifdef CIMPC_WITH_IP_V3
+  if constexpr (ip2_supported<D>()) {
+    if (ip_kernel_version() == 3)
+      return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm,
+                                                           ip_solve2_kernel<D, ip2_threads<D>(), ip2_minctas<D>()>,
+                                                           ip2_threads<D>(), KernelSmem2<D, ip2_threads<D>()>::BYTES);
+  }
+#endif
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, ip_solve_kernel<D, ip_threads<D>()>, ip_threads<D>(),
                                                        KernelSmem<D, ip_threads<D>()>::BYTES);
 }
 
 template <class D>
 cudaError_t launch_ip(const IpParams& p, int sm_count, cudaStream_t s) {
-  constexpr int PPW = 32 / D::G;
-  constexpr int PPB = PPW * (ip_threads<D>() / 32);  // subproblems in flight per CTA
   int occ = 1;
   cudaError_t e = occupancy_ip<D>(&occ);
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorLaunchOutOfResources;
   // persistent grid: one wave of resident CTAs, each owning a contiguous slice of the batch
   // (a slice of >= 4 passes keeps the knot constants staged in shared memory amortised)
+#ifdef CIMPC_WITH_IP_V3
+  if constexpr (ip2_supported<D>()) {
+    if (ip_kernel_version() == 3) {
+      constexpr int PPB = ip2_threads<D>() / (D::G / 2);  // subproblems in flight per CTA
+      const int64_t need = (p.n + 4 * PPB - 1) / (4 * PPB), cap = (int64_t)sm_count * occ;
+      int grid = (int)(need < cap ? need : cap);
+      if (grid < 1) grid = 1;
+      ip_solve2_kernel<D, ip2_threads<D>(), ip2_minctas<D>()>
+          <<<grid, ip2_threads<D>(), KernelSmem2<D, ip2_threads<D>()>::BYTES, s>>>(p);
+      return cudaGetLastError();
+    }
+  }
+#endif
+  constexpr int PPW = 32 / D::G;
+  constexpr int PPB = PPW * (ip_threads<D>() / 32);  // subproblems in flight per CTA
   int64_t need = (p.n + 4 * PPB - 1) / (4 * PPB);
   int64_t cap = (int64_t)sm_count * occ;
   int grid = (int)(need < cap ? need : cap);
