@@ -22,7 +22,7 @@ SYMBOLS = [
     "cimpc_sim_step_batch", "cimpc_linearize", "cimpc_get_linearization",
     "cimpc_newton_create_ex", "cimpc_newton_solve_batch_ex", "cimpc_newton_solve_batch_ex2",
     "cimpc_newton_solve_batch_host", "cimpc_sim_step_batch_ex", "cimpc_newton_create_dense", "cimpc_create_named", "cimpc_ip_solve_batch_host_ex",
-    "cimpc_nccl_get_unique_id", "cimpc_comm_init", "cimpc_gather",
+    "cimpc_nccl_get_unique_id", "cimpc_comm_init", "cimpc_gather", "cimpc_sim_steps_batch",
 ]
 
 
@@ -113,6 +113,9 @@ def load_library(path: str = LIB_PATH):
     lib.cimpc_sim_step_batch_ex.argtypes = [vp, i64, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.POINTER(IPOpts), dp, dp,
                                             dp, dp, dp, dp, vp]
     lib.cimpc_sim_step_batch_ex.restype = C.c_int
+    lib.cimpc_sim_steps_batch.argtypes = [vp, i64, i32, dp, dp, dp, dp, dp, C.c_double, C.c_double, C.POINTER(IPOpts), dp,
+                                          dp, dp, dp, dp, dp, vp]
+    lib.cimpc_sim_steps_batch.restype = C.c_int
     lib.cimpc_newton_create_ex.argtypes = [vp, i32, i64, dp, dp, dp, dp, dp, C.c_double, C.POINTER(NewtonOpts),
                                            C.POINTER(IPOpts)]
     lib.cimpc_newton_create_ex.restype = C.c_int

@@ -1259,10 +1259,10 @@ int cimpc_sim_step_batch(cimpc_ctx* ctx, int64_t n, const double* q0, const doub
   return cimpc_sim_step_batch_ex(ctx, n, q0, q1, u, w, active, mu, h, opts, q2, gamma, b, nullptr, status, iters, stream);
 }
 
-int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n, const double* q0, const double* q1, const double* u, const double* w,
-                            const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts, double* q2,
-                            double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters, void* stream) {
-  if (!ctx || n < 0 || n > (1 << 30) || !opts) return CIMPC_ERR_INVALID_ARGUMENT;
+static int sim_steps_impl(cimpc_ctx* ctx, int64_t n, int32_t n_steps, bool multi, const double* q0, const double* q1, const double* u,
+                          const double* w, const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts, double* q2,
+                          double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters, void* stream) {
+  if (!ctx || n < 0 || n > (1 << 30) || !opts || n_steps < 1 || n_steps > 4096) return CIMPC_ERR_INVALID_ARGUMENT;
   if (n == 0) return CIMPC_OK;
   if (!q0 || !q1 || !u || !q2 || !gamma || !b || !status || !iters) return CIMPC_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(ctx->device));
@@ -1276,10 +1276,25 @@ int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n, const double* q0, const d
   SimParams p;
   p.R = (int)n; p.q0 = q0; p.q1 = q1; p.u = u; p.w = w; p.active = active; p.mu = mu; p.h = h; p.o = *opts;
   p.q2_out = q2; p.gamma_out = gamma; p.b_out = b; p.phi_out = phi; p.status = status; p.iters = iters; p.scratch = ctx->sim_scratch;
+  p.nsteps = n_steps;
+  p.multi = multi ? 1 : 0;
   cudaError_t e = ctx->entry->sim_step(p, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(ctx, e, "sim_step_kernel launch");
   ctx->launches++;
   return CIMPC_OK;
+}
+
+int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n, const double* q0, const double* q1, const double* u, const double* w,
+                            const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts, double* q2,
+                            double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters, void* stream) {
+  return sim_steps_impl(ctx, n, 1, false, q0, q1, u, w, active, mu, h, opts, q2, gamma, b, phi, status, iters, stream);
+}
+
+int cimpc_sim_steps_batch(cimpc_ctx* ctx, int64_t n, int32_t n_steps, const double* q0, const double* q1, const double* u,
+                          const double* w, const uint8_t* active, double mu, double h, const cimpc_ip_opts* opts, double* q2,
+                          double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters, void* stream) {
+  // (n_steps = 1 keeps the multi-step conventions: failed / inactive rollouts get defined outputs)
+  return sim_steps_impl(ctx, n, n_steps, true, q0, q1, u, w, active, mu, h, opts, q2, gamma, b, phi, status, iters, stream);
 }
 
 

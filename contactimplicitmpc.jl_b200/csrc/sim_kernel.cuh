@@ -49,6 +49,11 @@ struct SimParams {
   uint8_t* status;    // R
   int32_t* iters;     // R
   double* scratch;    // per tile of 32 rollouts: SimLayout::TILE × 32 doubles
+  // several simulator steps under one held control (cimpc_sim_steps_batch): step s reads q_{t+s}, q_{t+s+1} from the
+  // outputs of the steps before it, w + s·R·nw, and writes its outputs at offset s·R·(row length); a tile runs its
+  // steps back to back, so a slow rollout delays only its own tile.  0 / 1 = the single step above.
+  int nsteps = 1;
+  int multi = 0;  // conventions of the multi-step entry point for failed / inactive rollouts (defined outputs)
 };
 
 template <class GEN>
@@ -213,8 +218,9 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int tile = blockIdx.x;
   const int rr = tile * 32 + lane;  // the rollout lane `lane` of every warp mirrors
-  const bool valid = rr < p.R && (p.active == nullptr || p.active[rr] != 0);
+  bool valid = rr < p.R && (p.active == nullptr || p.active[rr] != 0);  // rollout still running (mirrored by every warp)
   const int rc = (rr < p.R) ? rr : p.R - 1;
+  const int nsteps = p.nsteps > 1 ? p.nsteps : 1;
   const cimpc_ip_opts o = p.o;
 
   extern __shared__ __align__(16) double sm[];
@@ -238,17 +244,24 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
   auto th = [&](int i) { return S(L::O_TH, i); };
   auto tr = [&](int i) { return S(L::O_TR, i); };
 
+  for (int step = 0; step < nsteps; ++step) {
+  // step s > 0 of a multi-step launch continues from the configurations this CTA wrote at the end of steps s − 1, s − 2
+  const size_t so = (size_t)step * p.R;  // row offset of this step's outputs
+  const double* q0s = step == 0 ? p.q0 : (step == 1 ? p.q1 : p.q2_out + (so - 2 * (size_t)p.R) * NQ);
+  const double* q1s = step == 0 ? p.q1 : p.q2_out + (so - (size_t)p.R) * NQ;
+  const double* ws = p.w ? p.w + so * NW : nullptr;
+  if (step > 0) __syncthreads();  // the outputs of the previous step (global memory, written by warp 0) are visible
   // ---- θ = [q_t; q_{t+1}; u; w; μ; h]; z = 1, z[q] = q_{t+1}  (initialize_z!, initialize_θ!) ----
   for (int e = wid; e < NTH; e += WARPS) {
     double v;
-    if (e < NQ) v = p.q0[(size_t)rc * NQ + e];
-    else if (e < 2 * NQ) v = p.q1[(size_t)rc * NQ + e - NQ];
+    if (e < NQ) v = q0s[(size_t)rc * NQ + e];
+    else if (e < 2 * NQ) v = q1s[(size_t)rc * NQ + e - NQ];
     else if (e < 2 * NQ + NU) v = p.u[(size_t)rc * NU + e - 2 * NQ];
-    else if (e < 2 * NQ + NU + NW) v = p.w ? p.w[(size_t)rc * NW + e - 2 * NQ - NU] : 0.0;
+    else if (e < 2 * NQ + NU + NW) v = ws ? ws[(size_t)rc * NW + e - 2 * NQ - NU] : 0.0;
     else v = (e == 2 * NQ + NU + NW) ? p.mu : p.h;
     S(L::O_TH, e) = v;
   }
-  for (int e = wid; e < NZ; e += WARPS) S(L::O_Z, e) = (e < NQ) ? p.q1[(size_t)rc * NQ + e] : 1.0;
+  for (int e = wid; e < NZ; e += WARPS) S(L::O_Z, e) = (e < NQ) ? q1s[(size_t)rc * NQ + e] : 1.0;
   __syncthreads();
 
   // The loop is rotated so that the generated residual has ONE call site: trip 0 evaluates r(z) (α = 0,
@@ -523,22 +536,41 @@ __global__ void __launch_bounds__(GEN::NS * 32, MIN_CTAS) sim_step_kernel(const 
     alpha = done ? 0.0 : alpha_s[lane];
   }
   __syncthreads();  // the last z update was spread over the warps
+  const bool conv = (r_vio < o.r_tol) && (k_vio < o.kappa_tol);
   if (wid == 0 && valid) {
-    const bool conv = (r_vio < o.r_tol) && (k_vio < o.kappa_tol);
-    p.status[rr] = conv ? 1 : 0;
-    p.iters[rr] = iters;
-    for (int e = 0; e < NQ; ++e) p.q2_out[(size_t)rr * NQ + e] = S(L::O_Z, e);
-    for (int e = 0; e < NC; ++e) p.gamma_out[(size_t)rr * NC + e] = S(L::O_Z, NQ + e);
-    for (int e = 0; e < NB; ++e) p.b_out[(size_t)rr * NB + e] = S(L::O_Z, NQ + NC + e);
+    p.status[so + rr] = conv ? 1 : 0;
+    p.iters[so + rr] = iters;
+    // multi-step launch: a failed step leaves the rollout where it was (what the host loop does with a failed step)
+    const bool freeze = p.multi && !conv;
+    for (int e = 0; e < NQ; ++e) p.q2_out[(so + rr) * NQ + e] = freeze ? q1s[(size_t)rr * NQ + e] : S(L::O_Z, e);
+    for (int e = 0; e < NC; ++e) p.gamma_out[(so + rr) * NC + e] = S(L::O_Z, NQ + e);
+    for (int e = 0; e < NB; ++e) p.b_out[(so + rr) * NB + e] = S(L::O_Z, NQ + NC + e);
     if (p.phi_out != nullptr)
       for (int e = 0; e < NC; ++e) {
         // on a terrain s1 is the distance to the surface; `update_altitude!` evaluates ϕ of the POLICY's flat-ground model
         // (mpc_utils.jl:127: ϕ_func(s.model, s.env, q)), i.e. the height of the contact point: s1 + surface height
         double v = S(L::O_Z, NQ + 2 * NC + NB + e);
         if constexpr (GEN::NTERR > 0) v += S(L::O_TR, 2 * (GEN::TERR0 + 2 * e));
-        p.phi_out[(size_t)rr * NC + e] = v;
+        p.phi_out[(so + rr) * NC + e] = v;
       }
   }
+  if (p.multi) {
+    // A rollout that is switched off, or whose step failed earlier in this launch (RoboDojo `simulate!` stops at the
+    // first failed step), stays where it is: q_{t+2} = q_{t+1}, zero forces, status 0 — the chain of configurations
+    // the next step reads stays defined.  A rollout that fails THIS step reports the forces of the iterate it ended on
+    // (as the single-step call does), q_{t+2} = q_{t+1}, and is skipped from the next step on.
+    if (wid == 0 && !valid && rr < p.R) {
+      p.status[so + rr] = 0;
+      p.iters[so + rr] = 0;
+      for (int e = 0; e < NQ; ++e) p.q2_out[(so + rr) * NQ + e] = q1s[(size_t)rr * NQ + e];
+      for (int e = 0; e < NC; ++e) p.gamma_out[(so + rr) * NC + e] = 0.0;
+      for (int e = 0; e < NB; ++e) p.b_out[(so + rr) * NB + e] = 0.0;
+      if (p.phi_out != nullptr)
+        for (int e = 0; e < NC; ++e) p.phi_out[(so + rr) * NC + e] = 0.0;
+    }
+    valid = valid && conv;  // identical in every warp (mirrored scalars)
+  }
+  }  // step
 }
 
 }  // namespace cimpc

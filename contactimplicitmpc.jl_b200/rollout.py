@@ -59,7 +59,7 @@ class MonteCarloRollouts:
                  kappa, n_rollouts, newton_opts: NewtonOptions | None = None,
                  sim_opts: InteriorPointOptions | None = None, obj_gamma=None, obj_b=None, obj_v=None,
                  ref_gamma=None, ref_b=None, altitude_update: bool = False, altitude_impact_threshold: float = 1.0,
-                 sim_model: str | None = None, **newton_kw):
+                 sim_model: str | None = None, fused_steps: bool = True, **newton_kw):
         """obj_gamma / obj_b / ref_gamma / ref_b: required when `im_traj.mode == "configurationforce"`;
         obj_v: velocity weights of a TrackingVelocityObjective (the flamingo policy, examples/flamingo/flat.jl:34-41);
         altitude_update / altitude_impact_threshold: `CIMPCOptions` (src/controller/policy.jl:1-14) — every policy
@@ -75,6 +75,9 @@ class MonteCarloRollouts:
         # sim_model: the simulated plant, e.g. "quadruped_payload" under a policy built on the nominal robot
         self.sim = Simulator(im_traj.nq, im_traj.nu, im_traj.nw, im_traj.nc, im_traj.nb, opts=sim_opts or simulator_options(),
                              device=im_traj.device, model=sim_model)
+        # fused_steps: the N_sample simulator steps between two policy calls as ONE launch (`cimpc_sim_steps_batch`);
+        # False = one launch per step (same results bit for bit; kept for A/B runs and as the reference of the test)
+        self.fused_steps = bool(fused_steps)
         self.mpc_steps = 0
 
     def run(self, q1, v1, H_sim, record_every: int = 1, dist=None):
@@ -99,7 +102,6 @@ class MonteCarloRollouts:
         failed_at = torch.zeros(R, dtype=torch.int32, device=dev)  # simulator step at which a rollout failed (0 = never)
         self.ref.reset()
         q0_mpc = torch.from_numpy(np.tile(self.ref.q0[0], (R, 1))).to(dev)
-        cnt = N
         u_sim = torch.zeros((R, nu), dtype=torch.float64, device=dev)
         self.mpc_steps = 0
         # `p.altitude` of every rollout, and the impact bookkeeping of `update_altitude!` over the last N simulator
@@ -108,46 +110,57 @@ class MonteCarloRollouts:
         g_max = torch.zeros((R, nc), dtype=torch.float64, device=dev)
         phi_at = torch.zeros((R, nc), dtype=torch.float64, device=dev)
         out["alt"] = alt
-        for t in range(1, H_sim + 1):
-            if cnt == N:
-                if self.altitude_update and t > 1:  # policy.jl:111-115
-                    hit = g_max > self.alt_threshold
-                    alt = torch.where(hit, phi_at, alt).contiguous()
-                    out["alt"] = alt
-                g_max.zero_()
-                u_mpc, _, _ = self.newton.solve(self.ref.window, self.ref.q[:self.H + 2], self.ref.u[:self.H], self.mu_mpc,
-                                                self.h, q0_mpc, qb, warm_start=t > 1, active=ok.to(torch.uint8),
-                                                ref_gamma=None if self.ref.gamma is None else self.ref.gamma[:self.H],
-                                                ref_b=None if self.ref.b is None else self.ref.b[:self.H], alt=alt)
-                u_sim = (u_mpc / N).contiguous()
-                self.ref.advance()
-                q0_mpc = qb
-                cnt = 0
-                self.mpc_steps += 1
-            cnt += 1
+        t = 1
+        while t <= H_sim:
+            # ---- policy (every N simulator steps; policy.jl:108-152) ----
+            if self.altitude_update and t > 1:  # policy.jl:111-115
+                hit = g_max > self.alt_threshold
+                alt = torch.where(hit, phi_at, alt).contiguous()
+                out["alt"] = alt
+            g_max.zero_()
+            okb = ok.to(torch.uint8)
+            u_mpc, _, _ = self.newton.solve(self.ref.window, self.ref.q[:self.H + 2], self.ref.u[:self.H], self.mu_mpc,
+                                            self.h, q0_mpc, qb, warm_start=t > 1, active=okb,
+                                            ref_gamma=None if self.ref.gamma is None else self.ref.gamma[:self.H],
+                                            ref_b=None if self.ref.b is None else self.ref.b[:self.H], alt=alt)
+            u_sim = (u_mpc / N).contiguous()
+            self.ref.advance()
+            q0_mpc = qb
+            self.mpc_steps += 1
+            # ---- the N simulator steps under this control ----
+            n = min(N, H_sim - t + 1)
             w = None
             if dist is not None:
-                wt = np.asarray(dist(t), dtype=np.float64)
-                w = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(wt, (R, self.im.nw)))).to(dev)
-            q2, gam, b, st, _, phi = self.sim.step(qa, qb, u_sim, self.mu_sim, h_sim, w=w, active=ok.to(torch.uint8),
-                                                   want_phi=True)
-            if self.altitude_update:  # first maximum wins (strict `>` in mpc_utils.jl:119)
-                better = gam > g_max
-                g_max = torch.where(better, gam, g_max)
-                phi_at = torch.where(better, phi, phi_at)
-            # a failed step ends that rollout (RoboDojo `simulate!` stops and returns false): it is frozen and
-            # skipped by both kernels from here on
-            st = st.bool() | ~ok
-            newly_failed = ok & ~st
-            if bool(newly_failed.any()):
-                failed_at[newly_failed] = t
-            ok &= st
-            q2 = torch.where(ok[:, None], q2, qb)
-            if t % record_every == 0:
-                k = t // record_every - 1
-                out["q"][k + 2] = q2
-                out["u"][k], out["gamma"][k], out["b"][k] = u_sim, gam, b
-            qa, qb = qb, q2
+                wt = np.stack([np.broadcast_to(np.asarray(dist(t + s_), dtype=np.float64), (R, self.im.nw)) for s_ in range(n)])
+                w = torch.from_numpy(np.ascontiguousarray(wt)).to(dev)
+            if self.fused_steps:
+                # one launch: every tile of rollouts runs its n steps back to back (a rollout at the iteration cap delays
+                # its own tile, not every step of the batch)
+                q2s, gams, bs, sts, _, phis = self.sim.steps(n, qa, qb, u_sim, self.mu_sim, h_sim, w=w, active=okb)
+            for s_ in range(n):
+                tt = t + s_
+                if self.fused_steps:
+                    q2, gam, b, st, phi = q2s[s_], gams[s_], bs[s_], sts[s_], phis[s_]
+                else:
+                    q2, gam, b, st, _, phi = self.sim.step(qa, qb, u_sim, self.mu_sim, h_sim, w=None if w is None else w[s_],
+                                                           active=ok.to(torch.uint8), want_phi=True)
+                if self.altitude_update:  # first maximum wins (strict `>` in mpc_utils.jl:119)
+                    better = gam > g_max
+                    g_max = torch.where(better, gam, g_max)
+                    phi_at = torch.where(better, phi, phi_at)
+                # a failed step ends that rollout (RoboDojo `simulate!` stops and returns false): it is frozen and
+                # skipped by both kernels from here on
+                st = st.bool() | ~ok
+                newly_failed = ok & ~st
+                failed_at = torch.where(newly_failed, torch.full_like(failed_at, tt), failed_at)
+                ok = ok & st
+                q2 = torch.where(ok[:, None], q2, qb)
+                if tt % record_every == 0:
+                    k = tt // record_every - 1
+                    out["q"][k + 2] = q2
+                    out["u"][k], out["gamma"][k], out["b"][k] = u_sim, gam, b
+                qa, qb = qb, q2
+            t += n
         out["status"] = ok
         out["failed_at"] = failed_at
         return out

@@ -404,6 +404,36 @@ class Simulator:
         return q2, gam, b, st, it
 
 
+    def steps(self, n_steps, q0, q1, u, mu, h, w=None, opts: InteriorPointOptions | None = None, stream=None, active=None):
+        """`n_steps` simulator steps under the held control `u` in ONE launch (`cimpc_sim_steps_batch`): the N_sample
+        `step!` calls between two calls of the policy.  w: (n_steps, R, nw) or None.  Returns step-major tensors
+        q2 (n_steps, R, nq), gamma (n_steps, R, nc), b (n_steps, R, nb), status (n_steps, R) uint8, iters (n_steps, R)
+        int32, phi (n_steps, R, nc).  A rollout whose step fails ends there (q2 = the configuration it stopped at from
+        then on, zero forces, status 0), as `simulate!` does."""
+        import torch
+        o = opts or self.opts
+        R, n = q0.shape[0], int(n_steps)
+        for t_, n_ in ((q0, self.nq), (q1, self.nq), (u, self.nu)):
+            assert t_.is_cuda and t_.dtype == torch.float64 and t_.is_contiguous() and t_.shape == (R, n_)
+        dev = q0.device
+        q2 = torch.empty((n, R, self.nq), dtype=torch.float64, device=dev)
+        gam = torch.empty((n, R, self.nc), dtype=torch.float64, device=dev)
+        b = torch.empty((n, R, self.nb), dtype=torch.float64, device=dev)
+        phi = torch.empty((n, R, self.nc), dtype=torch.float64, device=dev)
+        st = torch.empty((n, R), dtype=torch.uint8, device=dev)
+        it = torch.empty((n, R), dtype=torch.int32, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        if w is not None:
+            assert w.is_cuda and w.dtype == torch.float64 and w.is_contiguous() and w.shape == (n, R, self.nw)
+        co = o.to_c()
+        capi.check(self._ctx, self.lib.cimpc_sim_steps_batch(
+            self._ctx, R, n, q0.data_ptr(), q1.data_ptr(), u.data_ptr(), w.data_ptr() if w is not None else None,
+            active.data_ptr() if active is not None else None, float(mu), float(h), C.byref(co), q2.data_ptr(),
+            gam.data_ptr(), b.data_ptr(), phi.data_ptr(), st.data_ptr(), it.data_ptr(), C.c_void_p(stream)))
+        return q2, gam, b, st, it, phi
+
+
 def implicit_dynamics(im_traj: ImplicitTrajectory, knot, theta, q2, gamma=None, b=None, alt=None,
                       opts: InteriorPointOptions | None = None):
     """`implicit_dynamics!(im_traj, traj; window)` for a flat batch of (rollout × stage) problems.

@@ -267,6 +267,23 @@ int cimpc_sim_step_batch_ex(cimpc_ctx* ctx, int64_t n_rollouts, const double* q0
                             double* q2, double* gamma, double* b, double* phi, uint8_t* status, int32_t* iters,
                             void* stream);
 
+/* SEVERAL simulator steps under one held control — the N_sample `step!` calls RoboDojo's `simulate!` makes between two
+ * calls of the policy (`policy` returns the same u = u_mpc / N_sample for N_sample consecutive steps,
+ * src/controller/policy.jl:108-110, 141-150; loop: examples/centroidal_quadruped/continuous_policy_v2.jl:19-34) — in ONE
+ * launch.  Step s (0-based) solves with θ = [q_{t+s}; q_{t+s+1}; u; w_s; μ; h] where the configurations beyond q0, q1 are
+ * the q2 of the steps before it.  A tile of rollouts runs its n_steps steps back to back without waiting for the other
+ * tiles, so a rollout that needs the iteration cap delays its own tile instead of every step of the whole batch.
+ * DEVICE pointers, column-major, outputs step-major: q2 nq × n × n_steps, gamma nc × n × n_steps, b nb × n × n_steps,
+ * phi nc × n × n_steps or NULL, status n × n_steps (uint8), iters n × n_steps (int32); w nw × n × n_steps or NULL.
+ * Same arithmetic per rollout and step as n_steps calls of cimpc_sim_step_batch_ex (bit-identical results).  A rollout
+ * whose step fails (status 0) ends, as `simulate!` stops at the first failed step: that step reports the forces of the
+ * iterate it ended on and q2 = q_{t+s+1}; it is skipped afterwards.  Skipped rollouts (also `active` = 0) get defined
+ * outputs in every step: q2 = the configuration they stopped at, zero forces and phi, status 0, iters 0. */
+int cimpc_sim_steps_batch(cimpc_ctx* ctx, int64_t n_rollouts, int32_t n_steps, const double* q0, const double* q1,
+                          const double* u, const double* w, const uint8_t* active, double mu, double h,
+                          const cimpc_ip_opts* opts, double* q2, double* gamma, double* b, double* phi, uint8_t* status,
+                          int32_t* iters, void* stream);
+
 /*
  * General form of the two calls above: both modes of `ImplicitTrajectory` and both objectives.
  *   obj_gamma nc × H_mpc, obj_b nb × H_mpc   diagonals of `obj.γ[t]`, `obj.b[t]` — required in :configurationforce mode,

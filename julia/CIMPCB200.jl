@@ -215,6 +215,24 @@ function sim_step!(b::B200ImplicitTrajectory, q_t, q_tp1, u, q_tp2, γ, bb, stat
 end
 
 """
+    sim_steps!(b, n_steps, q_t, q_tp1, u, q_out, γ_out, b_out, ϕ_out, status, iters; w, active, μ, h, opts, stream)
+
+The `n_steps` (= `N_sample`) `step!` calls `simulate!` makes between two calls of the policy, under the held control `u`,
+in one launch (`cimpc_sim_steps_batch`): outputs are step-major (`q_out` nq × R × n_steps, …, `status` R × n_steps); a
+rollout whose step fails ends there.  Same results as `n_steps` calls of `sim_step!`.
+"""
+function sim_steps!(b::B200ImplicitTrajectory, n_steps::Integer, q_t, q_tp1, u, q_out, γ_out, b_out, ϕ_out, status, iters;
+        w = nothing, active = nothing, μ::Float64, h::Float64, opts::IPOpts, stream = C_NULL)
+    ptr(x) = x === nothing ? C_NULL : reinterpret(Ptr{Cvoid}, pointer(x))
+    R = size(q_t, 2)
+    check(b.ctx, ccall((:cimpc_sim_steps_batch, LIB), Cint,
+        (Ptr{Cvoid}, Int64, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64, Ref{IPOpts},
+         Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+        b.ctx, R, Int32(n_steps), ptr(q_t), ptr(q_tp1), ptr(u), ptr(w), ptr(active), μ, h, Ref(opts),
+        ptr(q_out), ptr(γ_out), ptr(b_out), ptr(ϕ_out), ptr(status), ptr(iters), stream))
+end
+
+"""
     policy!(b, p::CIMPC, q_tp1, u_out, t; active)
 
 Batched `policy(p, traj, t)` (policy.jl:98-152) for rollouts in lock-step: every `N_sample`-th call runs

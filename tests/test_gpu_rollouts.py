@@ -393,3 +393,86 @@ def test_flamingo_climbs_the_piecewise_terrain_on_device(cuda_device):
     assert np.all(a["alt"][0] > 0.1) and np.all(a["alt"][0] < lift + 0.06)
     b = loop(False, H_sim)
     assert (not b["status"][0]) or b["q"][-1, 0, 0] < q[-1, 0] - 0.3, "altitude_update = false should not get up the ramp"
+
+
+def test_fused_simulator_steps_are_bit_identical(cuda_device):
+    """`cimpc_sim_steps_batch` (the N_sample simulator steps between two policy calls in ONE launch, every tile of
+    rollouts running its steps back to back) against N_sample calls of the single step driven by the host loop of
+    `simulate!`: same bits in every output of every step — including rollouts that fail on the way (drop box: rear feet
+    below the ground), rollouts switched off from the start, and per-step disturbances."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait
+    robot = "quadruped"
+    gait = load_gait(robot)
+    nq, nu, nw, nc, nb = SIZES[robot]
+    R, n = 200, 5
+    sim = cb.Simulator(nq, nu, nw, nc, nb)
+    h = gait["h"] / n
+    q1n = cb.quadruped_initial_configurations(R, seed=11)
+    q1n[:8, 2] += 0.6                                     # pitched torsos: steps that fail
+    q1 = torch.from_numpy(q1n).to(cuda_device)
+    q0 = (q1 - h * torch.from_numpy(np.tile((gait["q"][1] - gait["q"][0]) / gait["h"], (R, 1))).to(cuda_device)).contiguous()
+    u = torch.from_numpy(np.tile(gait["u"][0] / n, (R, 1))).to(cuda_device)
+    active = torch.ones(R, dtype=torch.uint8, device=cuda_device)
+    active[5] = 0
+    active[77] = 0
+    rng = np.random.Generator(np.random.Philox(4))
+    w = torch.from_numpy(0.05 * rng.standard_normal((n, R, nw))).to(cuda_device)
+    so = cb.simulator_options()
+    capped = cb.InteriorPointOptions(r_tol=so.r_tol, kappa_tol=so.kappa_tol, max_ls=so.max_ls, eps_min=so.eps_min,
+                                     undercut=so.undercut, gamma_reg=so.gamma_reg, diff_sol=False, max_iter=9)
+    for opts, want_failures in ((None, False), (capped, True)):
+        q2s, gs, bs, sts, its, phis = sim.steps(n, q0, q1, u, gait["mu"], h, w=w, active=active, opts=opts)
+        torch.cuda.synchronize()
+        # the host loop of the single step (rollout.py, fused_steps = False)
+        ok = active.bool().clone()
+        qa, qb = q0, q1
+        n_failed = 0
+        for s in range(n):
+            q2, g, b, st, it, phi = sim.step(qa, qb, u, gait["mu"], h, w=w[s].contiguous(), active=ok.to(torch.uint8),
+                                             want_phi=True, opts=opts)
+            st = st.bool() & ok
+            q2 = torch.where(st[:, None], q2, qb)
+            run = ok  # rollouts that took this step
+            assert torch.equal(sts[s].bool(), st), s
+            assert torch.equal(q2s[s], q2), s
+            assert torch.equal(gs[s][run], g[run]) and torch.equal(bs[s][run], b[run]) and torch.equal(phis[s][run], phi[run]), s
+            assert torch.equal(its[s][run], it[run]), s
+            assert float(gs[s][~run].abs().sum()) == 0.0 and float(bs[s][~run].abs().sum()) == 0.0
+            assert int(its[s][~run].sum()) == 0
+            n_failed += int((ok & ~st).sum())
+            ok = st
+            qa, qb = qb, q2
+        if want_failures:  # an iteration cap of 9 ends the slower rollouts at different steps of the launch
+            assert n_failed >= 3 and int(ok.sum()) >= 3, (n_failed, int(ok.sum()))
+    sim.close()
+
+
+def test_fused_steps_closed_loop_is_bit_identical(cuda_device):
+    """The closed loop with fused simulator steps (default) against the loop that launches every step on its own."""
+    import torch
+    import cimpc_b200 as cb
+    from common import load_gait, load_lin
+    robot = "quadruped"
+    lin, gait = load_lin(robot), load_gait(robot)
+    nq, nu = SIZES[robot][0], SIZES[robot][1]
+    R, N = 96, 5
+    opts = cb.InteriorPointOptions(r_tol=1e-4, kappa_tol=1e-4, max_iter=100, diff_sol=True)
+    oq = np.tile(1e-2 * np.array([1.0, 0.02, 0.25] + [0.75] * (nq - 3)), (H_MPC, 1))
+    ou = np.tile(3e-2 * np.ones(nu), (H_MPC, 1))
+    q1 = torch.from_numpy(cb.quadruped_initial_configurations(R, seed=3)).to(cuda_device)
+    v1 = torch.from_numpy(np.tile((gait["q"][1] - gait["q"][0]) / gait["h"], (R, 1))).to(cuda_device)
+    outs = []
+    for fused in (True, False):
+        im = cb.ImplicitTrajectory(*SIZES[robot], lin["z0"], lin["th0"], lin["r0"], lin["rz0"], lin["rth0"],
+                                   mode="configuration", opts=opts)
+        mc = cb.MonteCarloRollouts(im, gait["q"], gait["u"], gait["mu"], 1.0, gait["h"], H_mpc=H_MPC, N_sample=N, obj_q=oq,
+                                   obj_u=ou, kappa=1e-4, n_rollouts=R, newton_opts=cb.NewtonOptions(r_tol=3e-4, max_iter=5),
+                                   altitude_update=True, fused_steps=fused)
+        out = mc.run(q1, v1, 3 * N + 2, record_every=1)   # the last interval is a short one
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in out.items() if v is not None})
+        assert mc.mpc_steps == 4
+    for k in ("q", "u", "gamma", "b", "status", "failed_at", "alt"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
