@@ -31,6 +31,7 @@
 #include <utility>
 
 #include "dims.cuh"
+#include "fastdiv.cuh"
 #include "../../include/cimpc_b200.h"
 
 namespace cimpc {
@@ -235,7 +236,7 @@ __device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l
       // every lane forms the reciprocal of ITS candidate while the pivot search is in flight; the winner
       // publishes it in the pivot slot of the row (that slot is read for nothing else), which takes the
       // MUFU + Newton-step latency of 1/pivot off the critical path between publish and update
-      const double myinv = __drcp_rn(c.M[u]);
+      const double myinv = rcp_fast(c.M[u]);
       const unsigned cand = unp ? ((unsigned)__double2hiint(c.M[u]) & 0x7fffffffu) + 1u : 0u;
       // group maximum: one REDUX per group of the warp (independent, so one REDUX latency) instead of a
       // log2(G)-deep shuffle chain on the critical path of every elimination step
@@ -321,8 +322,8 @@ template <class D>
 __device__ __forceinline__ double step_length(bool hy, double y1, double y2, double d1, double d2, double tau) {
   // largest α ≤ 1 with y − αΔ ≥ (1−τ) y on the orthant (fraction to the boundary)
   double a = 1.0;
-  if (hy && d1 > 0.0) a = fmin(a, tau * y1 / d1);
-  if (hy && d2 > 0.0) a = fmin(a, tau * y2 / d2);
+  if (hy && d1 > 0.0) a = fmin(a, div_fast(tau * y1, d1));
+  if (hy && d2 > 0.0) a = fmin(a, div_fast(tau * y2, d2));
   return gmin<D::G>(a);
 }
 
@@ -341,8 +342,9 @@ __device__ __forceinline__ void load_schur(Ctx<D>& c, const double* __restrict__
   using S = GroupScratch<D>;
   const bool hr = l < NR, hm = l < NRP, hp = hy && l >= NR;
   const double y1r = fmax(c.y1, reg), y2r = fmax(c.y2, reg);
-  c.wl = hy ? c.ry2 * y2r / y1r : 1.0;
-  if (hp) *reinterpret_cast<double2*>(sc + S::O_V + 2 * (l - NR)) = make_double2(1.0 / c.wl, c.wl);
+  c.wl = hy ? div_fast(c.ry2 * y2r, y1r) : 1.0;
+  const double iwl = rcp_fast(c.wl);
+  if (hp) *reinterpret_cast<double2*>(sc + S::O_V + 2 * (l - NR)) = make_double2(iwl, c.wl);
   __syncwarp();
   c.a1 = 1.0; c.a2 = 0.0; c.a3 = 0.0;
   c.dpiv = true;
@@ -352,7 +354,7 @@ __device__ __forceinline__ void load_schur(Ctx<D>& c, const double* __restrict__
     if (c.dpiv) {
       c.a2 = vw.x;
     } else if (l == c.b0) {
-      c.a2 = 1.0 / c.bv;
+      c.a2 = Ls[D::O_IBV0 + l];  // 1 / B[b0, c]: this lane is b0 (same bits as 1.0 / c.bv, prep_kernel divides the same pair)
       c.a1 = vw.y * c.a2;
     } else {
       c.a3 = -Ls[D::O_RHO + l];
@@ -360,7 +362,7 @@ __device__ __forceinline__ void load_schur(Ctx<D>& c, const double* __restrict__
   }
   if (hp) {  // ψ lanes: pivot choice of their own contact, a2 = 1/w_ψ
     c.dpiv = c.wl * fabs(Ls[D::O_IBV0 + l]) >= PSI_PIVOT_RATIO;
-    c.a2 = 1.0 / c.wl;
+    c.a2 = iwl;
   }
   {  // does THIS subproblem have a contact on its B pivot (group-uniform)
     const unsigned bal = __ballot_sync(FULL, !c.dpiv);
@@ -590,6 +592,7 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
   const bool hx = l < NX, hy = l < NY;
   double* sc = scratch + (size_t)(tid / G) * KS::GS;
   const cimpc_ip_opts o = p.o;
+  const double kappa_floor = o.kappa_tol / o.undercut;  // κ never goes below this (loop-invariant)
 
   // slot → subproblem (identity unless the launch is compacted).  32-bit arithmetic on purpose: a 64-bit division is
   // an out-of-line call in SASS, and with that call present this kernel computed garbage (bisected on B200, nvcc 12.9).
@@ -754,16 +757,16 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
 
         // ---- predictor (affine) direction: only Δy1, Δy2 are needed ----
         // (the five divisions by ŷ1 of one iteration share one correctly-rounded reciprocal)
-        const double iy1 = __drcp_rn(y1r);
+        const double iy1 = rcp_fast(y1r);
         double t = schur_solve<D>(c, Ls, sc, l, gshift, hy, hy ? cu - (c.rrst - c.ry2 * c.rbil * iy1) : 0.0);
         const double dy1a = -t;
         const double dy2a = hy ? (c.rbil - y2r * dy1a) * iy1 : 0.0;
         const double a_aff = step_length<D>(hy, c.y1, c.y2, dy1a, dy2a, 1.0);
-        const double mu = gsum<G>(hy ? c.y1 * c.y2 : 0.0) / (double)NY;
-        const double mu_aff = gsum<G>(hy ? (c.y1 - a_aff * dy1a) * (c.y2 - a_aff * dy2a) : 0.0) / (double)NY;
-        double sg = fmin(fmax(mu_aff / mu, 0.0), 1.0);
+        const double mu = over_n<NY>(gsum<G>(hy ? c.y1 * c.y2 : 0.0));
+        const double mu_aff = over_n<NY>(gsum<G>(hy ? (c.y1 - a_aff * dy1a) * (c.y2 - a_aff * dy2a) : 0.0));
+        double sg = fmin(fmax(div_fast(mu_aff, mu), 0.0), 1.0);
         sg = sg * sg * sg;
-        const double kap = fmax(sg * mu, o.kappa_tol / o.undercut);
+        const double kap = fmax(sg * mu, kappa_floor);
 
         // ---- corrector: rbil = y1∘y2 − κ + Δy1aff∘Δy2aff ----
         const double rbc = hy ? fma(c.y1, c.y2, -kap) + dy1a * dy2a : 0.0;
