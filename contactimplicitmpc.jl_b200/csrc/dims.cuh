@@ -84,12 +84,20 @@ struct Dims {
   static constexpr int O_B0U = O_RHOU + NRP;               // NRP          b0(c(j)), j itself for rows without ψ coupling
   static constexpr int O_W = O_B0U + NRP;                   // NCOL×NRP     W[k][c]   at c*NRP + k   (uniform reads)
   static constexpr int O_AR = O_W + NCOL * NRP;            // NCOL×G       AR[l][c]  at c*G + l
-  static constexpr int SMEM_DOUBLES = round_up(O_AR + NCOL * G, 2);
-  // Global-only part (touched once per subproblem, in the prologue; served by L1/L2):
-  static constexpr int O_C0 = SMEM_DOUBLES;                // G×2          {cdyn0[l], crst0[l]}
+  static constexpr int ITER_DOUBLES = round_up(O_AR + NCOL * G, 2);  // what the iteration itself reads
+  // Prologue part (touched once per subproblem: c = c0 + Rθ θ):
+  static constexpr int O_C0 = ITER_DOUBLES;                // G×2          {cdyn0[l], crst0[l]}
   static constexpr int O_RTH = O_C0 + G * 2;               // NTH×G×2      {Rθdyn[l][j], Rθrst[l][j]}
   static constexpr int LIN_DOUBLES = O_RTH + NTH * G * 2;
   static constexpr int LIN_STRIDE = round_up(LIN_DOUBLES, 16);  // 128 B multiples
+  // The instances that share a warp between subproblems (G <= 16: 9 KB of Rθ for the quadruped) stage the prologue part
+  // too: every subproblem reads all of it, and from L1 / L2 that was 5.7 GB of loads per 655 360-subproblem sweep behind
+  // `long_scoreboard` stalls.  The one-subproblem-per-warp instances (centroidal: 27 KB of Rθ on top of 96 KB) keep it in L2.
+#ifndef CIMPC_STAGE_RTH
+#define CIMPC_STAGE_RTH 1
+#endif
+  static constexpr bool RTH_IN_SMEM = CIMPC_STAGE_RTH && G <= 16;
+  static constexpr int SMEM_DOUBLES = RTH_IN_SMEM ? round_up(LIN_DOUBLES, 2) : ITER_DOUBLES;
   static_assert((SMEM_DOUBLES * 8) % 16 == 0, "bulk copy size must be a multiple of 16 B");
 };
 

@@ -672,7 +672,8 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
       phase ^= 1u;
       staged = kn;
     }
-    const double* __restrict__ Lg = p.lin + (int64_t)kn * D::LIN_STRIDE;  // global-only part (prologue)
+    // prologue constants: staged with the rest where they fit (dims.cuh), else read through L1 / L2
+    const double* __restrict__ Lg = D::RTH_IN_SMEM ? Ls : p.lin + (int64_t)kn * D::LIN_STRIDE;
 
     // ---- warps pull PPW subproblems at a time from the segment ----
     for (;;) {
@@ -693,12 +694,12 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
       for (int j = l; j < NTH; j += G) sc[S::O_XY + j] = p.theta[pi * NTH + j];
       __syncwarp();
       {
-        const double2 c00 = __ldg(reinterpret_cast<const double2*>(Lg + D::O_C0) + l);
+        const double2 c00 = reinterpret_cast<const double2*>(Lg + D::O_C0)[l];
         double cd = c00.x, cr = c00.y;
         const double2* R = reinterpret_cast<const double2*>(Lg + D::O_RTH) + l;
 #pragma unroll 2
         for (int j = 0; j < NTH; ++j) {
-          const double2 r = __ldg(R + j * G);
+          const double2 r = R[j * G];
           const double t = sc[S::O_XY + j];
           cd = fma(r.x, t, cd);
           cr = fma(r.y, t, cr);
