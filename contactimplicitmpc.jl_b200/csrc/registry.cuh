@@ -173,8 +173,11 @@ cudaError_t launch_linearize(const LinEvalParams& p, cudaStream_t s) {
 #ifndef CIMPC_IP_THREADS_SHARED
 #define CIMPC_IP_THREADS_SHARED 256  // CTA size of the instances that share a warp between subproblems (G < 32)
 #endif
+#ifndef CIMPC_IP_THREADS_G32
+#define CIMPC_IP_THREADS_G32 512  // CTA size of the one-subproblem-per-warp instances (G = 32)
+#endif
 template <class D>
-constexpr int ip_threads() { return D::G == 32 ? 512 : CIMPC_IP_THREADS_SHARED; }
+constexpr int ip_threads() { return D::G == 32 ? CIMPC_IP_THREADS_G32 : CIMPC_IP_THREADS_SHARED; }
 
 template <class D>
 LinLayout layout_of() {
