@@ -44,6 +44,12 @@
 #ifndef CIMPC_UNROLL_SENS
 #define CIMPC_UNROLL_SENS 2
 #endif
+#ifndef CIMPC_UNROLL_RES
+#define CIMPC_UNROLL_RES 4            // residual: trips of two terms
+#endif
+#ifndef CIMPC_UNROLL_PRO
+#define CIMPC_UNROLL_PRO 4            // prologue c = c0 + Rθ θ
+#endif
 #ifndef CIMPC_UNROLL_SENS_SCATTER
 #define CIMPC_UNROLL_SENS_SCATTER 4
 #endif
@@ -54,7 +60,8 @@ namespace cimpc {
 template <class D> struct Unroll {
   static constexpr bool R = D::G == 32;
   static constexpr int CA = R ? 1 : CIMPC_UNROLL_CA, DX = R ? 2 : CIMPC_UNROLL_DX, SENS = R ? 1 : CIMPC_UNROLL_SENS,
-                       SENS_SCATTER = R ? 1 : CIMPC_UNROLL_SENS_SCATTER;
+                       SENS_SCATTER = R ? 1 : CIMPC_UNROLL_SENS_SCATTER, RES = R ? 2 : CIMPC_UNROLL_RES,
+                       PRO = R ? 2 : CIMPC_UNROLL_PRO;
 };
 
 struct IpParams {
@@ -250,7 +257,7 @@ __device__ __forceinline__ void residual(const double* __restrict__ Ls, double* 
   double ad = cdyn, ar = fma(ry2, y2, crst), ad2 = 0.0, ar2 = 0.0;
   const double* R = Ls + D::O_RES + 2 * l;
   constexpr int NJ = NX + NY;
-#pragma unroll 2
+#pragma unroll Unroll<D>::RES
   for (int j = 0; j + 1 < NJ; j += 2) {
     const double2 v = lds2(sc + S::O_XY + j);
     const double2 c0 = lds2(R + (j)*G * 2), c1 = lds2(R + (j + 1) * G * 2);
@@ -762,7 +769,7 @@ __global__ void __launch_bounds__(THREADS, (D::G == 32 ? 1 : 2)) ip_solve_kernel
         const double2 c00 = reinterpret_cast<const double2*>(Lg + D::O_C0)[l];
         double cd = c00.x, cr = c00.y;
         const double2* R = reinterpret_cast<const double2*>(Lg + D::O_RTH) + l;
-#pragma unroll 2
+#pragma unroll Unroll<D>::PRO
         for (int j = 0; j < NTH; ++j) {
           const double2 r = R[j * G];
           const double t = sc[S::O_XY + j];
