@@ -50,6 +50,9 @@
 #ifndef CIMPC_UNROLL_PRO
 #define CIMPC_UNROLL_PRO 4            // prologue c = c0 + Rθ θ
 #endif
+#ifndef CIMPC_UNROLL_GJ
+#define CIMPC_UNROLL_GJ 1             // Gauss-Jordan: trips of four columns (1 = rolled, the row rotated by four per trip)
+#endif
 #ifndef CIMPC_UNROLL_SENS_SCATTER
 #define CIMPC_UNROLL_SENS_SCATTER 4
 #endif
@@ -61,7 +64,7 @@ template <class D> struct Unroll {
   static constexpr bool R = D::G == 32;
   static constexpr int CA = R ? 1 : CIMPC_UNROLL_CA, DX = R ? 2 : CIMPC_UNROLL_DX, SENS = R ? 1 : CIMPC_UNROLL_SENS,
                        SENS_SCATTER = R ? 1 : CIMPC_UNROLL_SENS_SCATTER, RES = R ? 2 : CIMPC_UNROLL_RES,
-                       PRO = R ? 2 : CIMPC_UNROLL_PRO;
+                       PRO = R ? 2 : CIMPC_UNROLL_PRO, GJ = R ? 1 : CIMPC_UNROLL_GJ;
 };
 
 struct IpParams {
@@ -297,7 +300,7 @@ __device__ __forceinline__ void invert(Ctx<D>& c, double* __restrict__ sc, int l
   using S = GroupScratch<D>;
   c.mystep = UNPIV;
   c.msc = 0.0;
-#pragma unroll 1
+#pragma unroll Unroll<D>::GJ
   for (int kb = 0; kb < NY; kb += 4) {
     static_for<0, 4>([&](auto U) {
       constexpr int u = decltype(U)::value;
