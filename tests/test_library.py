@@ -57,3 +57,32 @@ def test_product_package_does_not_import_oracle():
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace(
                     "oracle/ip.py", "").replace("oracle/", "") or True
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+def test_header_is_strict_c99_and_links_from_plain_c(tmp_path):
+    """The boundary is a C ABI: `include/cimpc_b200.h` must compile as strict C99 (no C++-isms, no torch / CUDA types) and
+    a plain C translation unit that takes the address of EVERY declared entry point must link against the shared library —
+    what a cgo / ccall / JNI binding needs.  (The program is not run: calling into the library needs a GPU.)"""
+    import shutil
+    import subprocess
+    import cimpc_b200 as cb
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    lib = cb.LIB_PATH if hasattr(cb, "LIB_PATH") else os.path.join(ROOT, "contactimplicitmpc.jl_b200", "lib", "libcimpc_b200.so")
+    names = _header_functions()
+    src = tmp_path / "abi.c"
+    body = "\n".join(f"  table[{i}] = (fn){n};" for i, n in enumerate(names))
+    src.write_text('#include "cimpc_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\n'
+                   f"int main(void) {{\n  fn table[{len(names)}];\n{body}\n"
+                   f"  cimpc_ip_opts o; cimpc_newton_opts n;\n  cimpc_ip_opts_default(&o); cimpc_newton_opts_default(&n);\n"
+                   f'  printf("%d %d %g\\n", cimpc_version(), (int)(table[{len(names) - 1}] != 0), o.r_tol + n.r_tol);\n  return 0;\n}}\n')
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-Wno-pedantic-ms-format",
+                        "-I", os.path.join(ROOT, "include"), str(src), "-L", os.path.dirname(lib), "-lcimpc_b200",
+                        "-Wl,-rpath," + os.path.dirname(lib), "-o", str(exe)], capture_output=True, text=True)
+    # ISO C forbids converting function pointers of different types only with -pedantic on some casts: the cast above is the
+    # one ISO C allows (function pointer to function pointer)
+    assert r.returncode == 0, r.stderr
+    # the host-only entry points run without a device
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.split()[0] == "100", out.stdout + out.stderr
